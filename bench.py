@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- training images/sec of the BTS hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N>1, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference algorithm on host cores
+
+Workload (config K16, BASELINE.json configs[1]): DenseNet-161 encoder, 352x704 synthetic RGB->depth, batch 16
+PER GPU (weak scaling), train mode (batch-stat BN), silog loss (lambda .85), backward, AdamW step with the two
+parameter groups and poly LR of bts_main.py:371-373,456-460.  A "step" = zero_grad + forward + loss + backward +
+optimizer step over one batch.  `value` is timed with inputs resident in HBM; `e2e` repeats the measurement with
+the batch starting in pinned host memory (H2D inside the timed region) and the loss read back (D2H) every step.
+`roofline` is the LPG plane-to-depth kernel pair (the kernel BASELINE.json's metric names), timed live with CUDA
+events on the launching stream; `roofline_step` relates the whole step to the conv-FLOP roof.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, B_PER_GPU = 352, 704, 16
+FOCAL = 721.5377
+MAX_DEPTH = 80.0
+GFLOP_PER_IMG_TRAIN = 588.0      # nominal conv FLOPs, fwd+dgrad+wgrad, DN-161 @352x704
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def synth_batch(B, seed, dev="cpu", pin=False):
+    """SURVEY 8d synthetic inputs: image randn, focal 721.5377 (float64 like the DataLoader collate), KITTI-like
+    sparse depth (20% valid, else 0)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, 3, H, W, generator=g)
+    gt = torch.rand(B, 1, H, W, generator=g) * MAX_DEPTH
+    gt = torch.where(torch.rand(B, 1, H, W, generator=g) < 0.2, gt, torch.zeros_like(gt))
+    focal = torch.full((B,), FOCAL, dtype=torch.float64)
+    if pin:
+        return img.pin_memory(), focal.pin_memory(), gt.pin_memory()
+    return img.to(dev), focal.to(dev), gt.to(dev)
+
+
+def make_optimizer(model, torch):
+    """bts_main.py:371-373 (lr 1e-4, eps 1e-3, wd 1e-2 encoder / 0 decoder: arguments_train_eigen.txt)."""
+    m = model.module if hasattr(model, "module") else model
+    return torch.optim.AdamW([{"params": m.encoder.parameters(), "weight_decay": 1e-2},
+                              {"params": m.decoder.parameters(), "weight_decay": 0}], lr=1e-4, eps=1e-3)
+
+
+def freeze_like_set_misc(model):
+    """bts_main.py:217-247 default: 'Fixing first conv layer' -> conv0 + every encoder BN affine param frozen."""
+    for name, p in model.encoder.named_parameters():
+        if any(x in name for x in ("conv0", "norm")):
+            p.requires_grad = False
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_steps(steps, warmup, B=2):
+    """The reference algorithm (oracle port of pytorch/bts.py; the Python reference itself does not travel to the
+    GPU box) on all host cores: DN-161, 352x704, one train step per sample batch of B images."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bts_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = O.OracleModel("densenet161_bts", MAX_DEPTH, "kitti", 512)
+    m.train()
+    opt = torch.optim.AdamW([{"params": m.encoder.parameters(), "weight_decay": 1e-2},
+                             {"params": m.decoder.parameters(), "weight_decay": 0}], lr=1e-4, eps=1e-3)
+    img, focal, gt = synth_batch(B, 1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = m(img, focal)
+        loss = O.silog(out[4], gt, gt > 1.0, 0.85)
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": B * len(times) / total, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "oracle/bts_oracle.py OracleModel (torch CPU fp32, %d threads), DN-161 352x704, B=%d train step "
+                      "(fwd+silog+bwd+AdamW), %d timed steps after %d warm-up" % (cores, B, len(times), warmup),
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def lpg_roofline(torch, dev, pk):
+    """LPG-u microbench (BASELINE.json configs[4]), HBM regime: r=8/4/2 at 1024^2, batch sized so the output is
+    512 MB (>> 126 MB L2).  fwd+bwd algorithmic bytes = B*H*W*(8 + 48/r^2)  (BASELINE.md section 3)."""
+    from bts_b200 import ops
+    import math
+    out = {}
+    for r in (8, 4, 2):
+        side, Bn = 1024, 128
+        h = side // r
+        g = torch.Generator(device=dev).manual_seed(r)
+        z = torch.randn(Bn, 3, h, h, device=dev, generator=g)
+        th = torch.sigmoid(z[:, 0]) * math.pi / 3
+        ph = torch.sigmoid(z[:, 1]) * math.pi * 2
+        plane = torch.stack([torch.sin(th) * torch.cos(ph), torch.sin(th) * torch.sin(ph), torch.cos(th),
+                             torch.sigmoid(z[:, 2]) * MAX_DEPTH], 1).contiguous().requires_grad_(True)
+        dy = torch.randn(Bn, side, side, device=dev, generator=g)
+        st = torch.cuda.current_stream()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf, tb = [], []
+        for it in range(3 + 10):
+            ev[0].record(st)
+            d = ops.lpg(plane, r)
+            ev[1].record(st)
+            (gp,) = torch.autograd.grad(d, plane, dy)
+            ev[2].record(st)
+            torch.cuda.synchronize()
+            if it >= 3:
+                tf.append(ev[0].elapsed_time(ev[1]))
+                tb.append(ev[1].elapsed_time(ev[2]))
+            del d, gp
+        px = Bn * side * side
+        bf, bb = 4.0 * px * (1 + 4.0 / r ** 2), 4.0 * px * (1 + 8.0 / r ** 2)
+        mf, mb = statistics.mean(tf), statistics.mean(tb)
+        out["r%d" % r] = {"fwd_gbs": bf / mf / 1e6, "bwd_gbs": bb / mb / 1e6, "fwd_bwd_gbs": (bf + bb) / (mf + mb) / 1e6,
+                          "fwd_ms": mf, "bwd_ms": mb, "shape": [Bn, side, side]}
+        del plane, dy, z
+    torch.cuda.empty_cache()
+    a = out["r8"]["fwd_bwd_gbs"]
+    return {"bound": "hbm", "kernel": "lpg_fwd_vec<8>+lpg_bwd_vec<8> (fwd+bwd, r=8, 128x1024x1024, output 512 MB >> L2)",
+            "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a / pk["hbm_gbs"], "peak_source": pk["source"],
+            "traffic": None, "sweep": out}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import bts
+    from bts_b200 import _lib
+    _lib.lib()                                   # fail loudly if the CUDA library is missing
+    torch.backends.cudnn.benchmark = True        # bts_main.py:402
+    torch.manual_seed(0)
+    p = types.SimpleNamespace(encoder="densenet161_bts", max_depth=MAX_DEPTH, dataset="kitti", bts_size=512,
+                              pretrained=False)
+    model = bts.BtsModel(p)
+    model.train()
+    model.decoder.apply(bts.weights_init_xavier)
+    freeze_like_set_misc(model)
+    model.to(dev)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    opt = make_optimizer(model, torch)
+    crit = bts.silog_loss(0.85)
+    B = B_PER_GPU
+    img, focal, gt = synth_batch(B, 1 + rank, dev)
+    himg, hfocal, hgt = synth_batch(B, 1 + rank, pin=True)
+    total_steps = 10000
+
+    def step(i, x, f, g):
+        opt.zero_grad()
+        out = model(x, f)
+        loss = crit(out[4], g, g > 1.0)
+        loss.backward()
+        lr = (1e-4 - 1e-5) * (1 - i / total_steps) ** 0.9 + 1e-5
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        opt.step()
+        return loss
+
+    def timed(fn, K, Wm):
+        for i in range(Wm):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = _lib.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = torch.cuda.current_stream()
+        e0.record(st)
+        for i in range(K):
+            fn(Wm + i)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        return float(ms), _lib.launches - l0, clocks
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    ms, launches, clocks = timed(lambda i: step(i, img, focal, gt), K, Wm)
+
+    def e2e_step(i):
+        x = himg.to(dev, non_blocking=True)
+        f = hfocal.to(dev, non_blocking=True)
+        g = hgt.to(dev, non_blocking=True)
+        return float(step(i, x, f, g))           # D2H read of the loss every step (bts_main.py:463)
+
+    ms_e, _, _ = timed(e2e_step, K, 1)
+    h2d = himg.numel() * 4 + hfocal.numel() * 8 + hgt.numel() * 4
+
+    pk = peaks()
+    res = {
+        "metric": "training images/sec (352x704, DenseNet-161)", "value": world * B * K / (ms / 1e3), "unit": "images/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "K16: DenseNet-161 encoder, 352x704 KITTI-shape synthetic, batch 16/GPU, train step "
+                               "(fwd + silog + bwd + AdamW), random-init weights",
+                   "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "no explicit flush: per-step working set (~31 GB saved activations) >> 126 MB L2",
+                   "conv_path": os.environ.get("BTS_B200_CONV", "auto")},
+        "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e / K},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0:
+        res["roofline_step"] = {"bound": "tensor", "achieved": res["value"] / world * GFLOP_PER_IMG_TRAIN / 1e3,
+                                "unit": "TFLOP/s per GPU (nominal conv FLOPs 588 GFLOP/img)",
+                                "peak": pk["bf16_tflops"] / 2.0 / 3.0,
+                                "peak_note": "parity-grade 3xTF32 = (bf16 sustained / 2) / 3; " + pk["source"],
+                                "frac": res["value"] / world * GFLOP_PER_IMG_TRAIN / 1e3 / (pk["bf16_tflops"] / 6.0)}
+        if world == 1:
+            if not args.no_lpg:
+                del model, opt
+                torch.cuda.empty_cache()
+                res["roofline"] = lpg_roofline(torch, dev, pk)
+            if not args.no_cpu:
+                res["cpu_baseline"] = cpu_reference_steps(3, 1)
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.steps, args.warmup)
+    res = {"impl": "reference", "metric": "training images/sec (352x704, DenseNet-161)", "value": r["value"],
+           "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "K16: DenseNet-161 encoder, 352x704 KITTI-shape synthetic, train step "
+                                  "(fwd + silog + bwd + AdamW); CPU sample batch = 2 images/step"},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(res), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

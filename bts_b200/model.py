@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference's module surface (pytorch/bts.py) over the B200 kernels.
+
+Same class names, constructor arguments, forward signatures, 5-tuple output and -- the checkpoint wire
+format -- the same state_dict keys and shapes, so the reference's bts_main.py /
+bts_test.py import this as `bts` unchanged.  The arithmetic underneath is ours:
+  * plane heads + LPG + /max_depth + nearest down-sample: one fused sm_100a kernel each way (ops.plane_head_lpg)
+  * silog loss: two streaming kernels (ops.silog)
+  * convolutions: the tcgen05 implicit-GEMM engine (bts_b200.conv) where enabled, cuDNN otherwise (scaffold)
+Reference lines are cited per class.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def bn_init_as_tf(m):
+    """reference pytorch/bts.py:26-31 -- BN layers behave like TF {'is_training': False, 'scale': True}."""
+    if isinstance(m, nn.BatchNorm2d):
+        m.track_running_stats = True
+        m.eval()
+        m.affine = True
+        m.requires_grad = True
+
+
+def weights_init_xavier(m):
+    """reference pytorch/bts.py:34-38 -- called as model.decoder.apply(weights_init_xavier) by bts_main.py:338."""
+    if isinstance(m, nn.Conv2d):
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+
+
+class silog_loss(nn.Module):
+    """reference pytorch/bts.py:41-48."""
+
+    def __init__(self, variance_focus):
+        super().__init__()
+        self.variance_focus = variance_focus
+
+    def forward(self, depth_est, depth_gt, mask):
+        return ops.silog(depth_est, depth_gt, mask, self.variance_focus)
+
+
+def _conv(cin, cout, k, dilation=1):
+    pad = dilation * (k // 2)
+    return nn.Conv2d(cin, cout, k, 1, pad, dilation=dilation, bias=False)
+
+
+class atrous_conv(nn.Sequential):
+    """reference pytorch/bts.py:51-66: [BN(eps 1.1e-5)] ReLU 1x1(C->2*out) BN ReLU 3x3 dilated (2*out->out)."""
+
+    def __init__(self, in_channels, out_channels, dilation, apply_bn_first=True):
+        super().__init__()
+        body = nn.Sequential()
+        if apply_bn_first:
+            body.add_module("first_bn", nn.BatchNorm2d(in_channels, momentum=0.01, affine=True,
+                                                       track_running_stats=True, eps=1.1e-5))
+        body.add_module("aconv_sequence", nn.Sequential(
+            nn.ReLU(),
+            _conv(in_channels, out_channels * 2, 1),
+            nn.BatchNorm2d(out_channels * 2, momentum=0.01, affine=True, track_running_stats=True),
+            nn.ReLU(),
+            _conv(out_channels * 2, out_channels, 3, dilation)))
+        self.atrous_conv = body
+
+    def forward(self, x):
+        return self.atrous_conv(x)
+
+
+class upconv(nn.Module):
+    """reference pytorch/bts.py:69-80: nearest x ratio -> 3x3 conv -> ELU."""
+
+    def __init__(self, in_channels, out_channels, ratio=2):
+        super().__init__()
+        self.elu = nn.ELU()
+        self.conv = _conv(in_channels, out_channels, 3)
+        self.ratio = ratio
+
+    def forward(self, x):
+        return self.elu(self.conv(F.interpolate(x, scale_factor=self.ratio, mode="nearest")))
+
+
+class reduction_1x1(nn.Sequential):
+    """reference pytorch/bts.py:83-122.  `trunk()` runs the 1x1+ELU chain and the last 1x1 conv; the decoder
+    feeds its 3-channel result to the fused head+LPG kernel.  `forward()` keeps the reference's public
+    behaviour (4-vector (n1,n2,n3,n4) for plane heads, sigmoid map for the final head)."""
+
+    def __init__(self, num_in_filters, num_out_filters, max_depth, is_final=False):
+        super().__init__()
+        self.max_depth = max_depth
+        self.is_final = is_final
+        self.sigmoid = nn.Sigmoid()
+        self.reduc = nn.Sequential()
+        cin, cout = num_in_filters, num_out_filters
+        while cout >= 4:
+            if cout < 8:
+                if is_final:
+                    self.reduc.add_module("final", nn.Sequential(_conv(cin, 1, 1), nn.Sigmoid()))
+                else:
+                    self.reduc.add_module("plane_params", _conv(cin, 3, 1))
+                break
+            self.reduc.add_module("inter_{}_{}".format(cin, cout), nn.Sequential(_conv(cin, cout, 1), nn.ELU()))
+            cin, cout = cout, cout // 2
+
+    def trunk(self, net):
+        return self.reduc(net)
+
+    def forward(self, net):
+        net = self.trunk(net)
+        if self.is_final:
+            return net
+        theta = torch.sigmoid(net[:, 0]) * math.pi / 3
+        phi = torch.sigmoid(net[:, 1]) * math.pi * 2
+        dist = torch.sigmoid(net[:, 2]) * self.max_depth
+        st = torch.sin(theta)
+        return torch.stack([st * torch.cos(phi), st * torch.sin(phi), torch.cos(theta), dist], dim=1)
+
+
+class local_planar_guidance(nn.Module):
+    """reference pytorch/bts.py:124-146.  `focal` is accepted and ignored, as in the reference (Q1)."""
+
+    def __init__(self, upratio):
+        super().__init__()
+        self.upratio = float(upratio)
+        k = torch.arange(int(upratio)).float()
+        self.u = k.reshape(1, 1, -1)
+        self.v = k.reshape(1, -1, 1)
+
+    def forward(self, plane_eq, focal=None):
+        return ops.lpg(plane_eq, int(self.upratio))
+
+
+class bts(nn.Module):
+    """The decoder, reference pytorch/bts.py:148-266."""
+
+    def __init__(self, params, feat_out_channels, num_features=512):
+        super().__init__()
+        self.params = params
+        f, nf = feat_out_channels, num_features
+        self.upconv5 = upconv(f[4], nf)
+        self.bn5 = nn.BatchNorm2d(nf, momentum=0.01, affine=True, eps=1.1e-5)
+        self.conv5 = nn.Sequential(_conv(nf + f[3], nf, 3), nn.ELU())
+        self.upconv4 = upconv(nf, nf // 2)
+        self.bn4 = nn.BatchNorm2d(nf // 2, momentum=0.01, affine=True, eps=1.1e-5)
+        self.conv4 = nn.Sequential(_conv(nf // 2 + f[2], nf // 2, 3), nn.ELU())
+        self.bn4_2 = nn.BatchNorm2d(nf // 2, momentum=0.01, affine=True, eps=1.1e-5)
+        self.daspp_3 = atrous_conv(nf // 2, nf // 4, 3, apply_bn_first=False)
+        self.daspp_6 = atrous_conv(nf // 2 + nf // 4 + f[2], nf // 4, 6)
+        self.daspp_12 = atrous_conv(nf + f[2], nf // 4, 12)
+        self.daspp_18 = atrous_conv(nf + nf // 4 + f[2], nf // 4, 18)
+        self.daspp_24 = atrous_conv(nf + nf // 2 + f[2], nf // 4, 24)
+        self.daspp_conv = nn.Sequential(_conv(nf + nf // 2 + nf // 4, nf // 4, 3), nn.ELU())
+        self.reduc8x8 = reduction_1x1(nf // 4, nf // 4, params.max_depth)
+        self.lpg8x8 = local_planar_guidance(8)
+        self.upconv3 = upconv(nf // 4, nf // 4)
+        self.bn3 = nn.BatchNorm2d(nf // 4, momentum=0.01, affine=True, eps=1.1e-5)
+        self.conv3 = nn.Sequential(_conv(nf // 4 + f[1] + 1, nf // 4, 3), nn.ELU())
+        self.reduc4x4 = reduction_1x1(nf // 4, nf // 8, params.max_depth)
+        self.lpg4x4 = local_planar_guidance(4)
+        self.upconv2 = upconv(nf // 4, nf // 8)
+        self.bn2 = nn.BatchNorm2d(nf // 8, momentum=0.01, affine=True, eps=1.1e-5)
+        self.conv2 = nn.Sequential(_conv(nf // 8 + f[0] + 1, nf // 8, 3), nn.ELU())
+        self.reduc2x2 = reduction_1x1(nf // 8, nf // 16, params.max_depth)
+        self.lpg2x2 = local_planar_guidance(2)
+        self.upconv1 = upconv(nf // 8, nf // 16)
+        self.reduc1x1 = reduction_1x1(nf // 16, nf // 32, params.max_depth, is_final=True)
+        self.conv1 = nn.Sequential(_conv(nf // 16 + 4, nf // 16, 3), nn.ELU())
+        self.get_depth = nn.Sequential(_conv(nf // 16, 1, 3), nn.Sigmoid())
+
+    def forward(self, features, focal):
+        skip0, skip1, skip2, skip3 = features[0], features[1], features[2], features[3]
+        md = self.params.max_depth
+        x = self.bn5(self.upconv5(F.relu(features[4])))                                   # H/16
+        x = self.conv5(torch.cat([x, skip3], 1))
+        cat4 = torch.cat([self.bn4(self.upconv4(x)), skip2], 1)                           # H/8
+        iconv4 = self.bn4_2(self.conv4(cat4))
+        d3 = self.daspp_3(iconv4)
+        grow = torch.cat([cat4, d3], 1)
+        d6 = self.daspp_6(grow)
+        grow = torch.cat([grow, d6], 1)
+        d12 = self.daspp_12(grow)
+        grow = torch.cat([grow, d12], 1)
+        d18 = self.daspp_18(grow)
+        grow = torch.cat([grow, d18], 1)
+        d24 = self.daspp_24(grow)
+        feat8 = self.daspp_conv(torch.cat([iconv4, d3, d6, d12, d18, d24], 1))
+
+        depth_8x8_scaled, d8_ds = ops.plane_head_lpg(self.reduc8x8.trunk(feat8), 8, md, ds_stride=4)
+        x = self.bn3(self.upconv3(feat8))                                                 # H/4
+        iconv3 = self.conv3(torch.cat([x, skip1, d8_ds], 1))
+        depth_4x4_scaled, d4_ds = ops.plane_head_lpg(self.reduc4x4.trunk(iconv3), 4, md, ds_stride=2)
+        x = self.bn2(self.upconv2(iconv3))                                                # H/2
+        iconv2 = self.conv2(torch.cat([x, skip0, d4_ds], 1))
+        depth_2x2_scaled = ops.plane_head_lpg(self.reduc2x2.trunk(iconv2), 2, md)
+        up1 = self.upconv1(iconv2)                                                        # H
+        reduc1x1 = self.reduc1x1(up1)
+        iconv1 = self.conv1(torch.cat([up1, reduc1x1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled], 1))
+        final_depth = md * self.get_depth(iconv1)
+        if self.params.dataset == "kitti":
+            final_depth = final_depth * focal.view(-1, 1, 1, 1).float() / 715.0873
+        return depth_8x8_scaled, depth_4x4_scaled, depth_2x2_scaled, reduc1x1, final_depth
+
+
+_ENCODERS = {
+    # params.encoder: (torchvision ctor, use .features, skip tap names, skip channels)   reference bts.py:273-300
+    "densenet121_bts": ("densenet121", True, ["relu0", "pool0", "transition1", "transition2", "norm5"], [64, 64, 128, 256, 1024]),
+    "densenet161_bts": ("densenet161", True, ["relu0", "pool0", "transition1", "transition2", "norm5"], [96, 96, 192, 384, 2208]),
+    "resnet50_bts": ("resnet50", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
+    "resnet101_bts": ("resnet101", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
+    "resnext50_bts": ("resnext50_32x4d", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
+    "resnext101_bts": ("resnext101_32x8d", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
+    "mobilenetv2_bts": ("mobilenet_v2", True, [], [16, 24, 32, 64, 1280]),
+}
+
+
+def _load_backbone(ctor, pretrained):
+    """The reference asks torchvision for ImageNet weights (pretrained=True, bts.py:274-298).  We honour that
+    when the checkpoint is already in the local torch-hub cache (or params.pretrained=True forces a download);
+    offline with an empty cache -- the benchmark / test condition -- the backbone is random-initialised."""
+    import os
+    import torchvision.models as tvm
+    fn = getattr(tvm, ctor)
+    if pretrained is not False:
+        try:
+            w = tvm.get_model_weights(ctor).DEFAULT
+            cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
+            if pretrained is True or os.path.isfile(cached):
+                return fn(weights=w)
+        except Exception as e:
+            print("bts_b200: pretrained %s weights unavailable (%s); using random init" % (ctor, type(e).__name__))
+    return fn(weights=None)
+
+
+class encoder(nn.Module):
+    """reference pytorch/bts.py:268-320.  The backbone modules (and therefore parameter names, which
+    bts_main.set_misc freezes by substring, bts_main.py:222-247) are torchvision's, as in the reference.
+    params.pretrained: None (default) = use cached ImageNet weights if present, True = force, False = random."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.params = params
+        if params.encoder not in _ENCODERS:
+            print("Not supported encoder: {}".format(params.encoder))
+            return
+        ctor, feats, names, ch = _ENCODERS[params.encoder]
+        m = _load_backbone(ctor, getattr(params, "pretrained", None))
+        self.base_model = m.features if feats else m
+        self.feat_names = names
+        self.feat_out_channels = ch
+        if params.encoder == "mobilenetv2_bts":
+            self.feat_inds = [2, 4, 7, 11, 19]
+
+    def forward(self, x):
+        skips = []
+        mobile = self.params.encoder == "mobilenetv2_bts"
+        for i, (k, v) in enumerate(self.base_model._modules.items(), start=1):
+            if "fc" in k or "avgpool" in k:
+                continue
+            x = v(x)
+            if mobile:
+                if i in (2, 4, 7, 11, 19):
+                    skips.append(x)
+            elif any(n in k for n in self.feat_names):
+                skips.append(x)
+        return skips
+
+
+class BtsModel(nn.Module):
+    """reference pytorch/bts.py:323-331."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.encoder = encoder(params)
+        self.decoder = bts(params, self.encoder.feat_out_channels, params.bts_size)
+
+    def forward(self, x, focal):
+        return self.decoder(self.encoder(x), focal)
