@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out.decode()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcuda"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     subprocess.check_call(cmd)
     return LIB_PATH
 
@@ -73,7 +73,15 @@ SIGNATURES = {
     "bts_silog_bwd": [_p, _p, _p, _ll, _f, _p, _p, _p, _p],
     "bts_plane_head_fwd": [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p],
     "bts_plane_head_bwd": [_p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _p],
+    "bts_conv_n_tile": [_i],
+    "bts_conv_packed_floats": [_i, _i, _i, _i],
+    "bts_conv_pack_weights": [_p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _p],
+    "bts_conv_fwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _ll, _i, _i, _p],
+    "bts_conv_wgrad_plan": [_i, _i, _i, _i, _i, _i, _i, _p, _p],
+    "bts_conv_wgrad": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _i, _p, _i, _p, _ll, _ll,
+                       _ll, _ll, _i, _p],
 }
+RESTYPES = {"bts_conv_packed_floats": ctypes.c_longlong}
 
 
 def lib():
@@ -88,7 +96,7 @@ def lib():
         for name, args in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the symbol is missing
             fn.argtypes = args
-            fn.restype = ctypes.c_int
+            fn.restype = RESTYPES.get(name, ctypes.c_int)
         _lib = L
     return _lib
 

@@ -1,0 +1,414 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a, parity-grade 3xTF32.
+//
+// Replaces the cuDNN convolution (+ separate BN-apply / ReLU / ELU / nearest-upsample ATen kernels) behind every
+// 1x1 / 3x3 / dilated conv of the BTS decoder and the torchvision encoder (reference pytorch/bts.py:51-80,153-194).
+//
+//   out[p, co] = act( sum_{tap, ci}  pre(x[p (+) tap, ci]) * w[co, ci, tap] )         NHWC activations
+//       pre  = optional per-input-channel affine (a folded BatchNorm: x*scale+shift) and/or ReLU, applied to the
+//              A operand on its way into shared memory; zero padding is applied AFTER pre (as conv2d pads the
+//              normalised tensor);  (+) includes stride, dilation and an optional nearest x2 up-sample of the source
+//              (upconv, bts.py:77) which is folded into the address map -- the 4x tensor is never materialised.
+//       act  = none | ELU | sigmoid, fused in the epilogue.
+//
+// GEMM view: M = B*Hout*Wout pixels (128 per CTA tile = the 128 TMEM lanes), N = Cout (<=128 per tile),
+// K = taps * Cin in blocks of 32 fp32 (one 128-byte swizzled row per pixel).
+// Precision: fp32 operands are split x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) and the tile
+// accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  with kind::tf32 MMAs into fp32 TMEM accumulators (error
+// ~2^-21 per product: fp32-grade).  Single-pass TF32 is available as an explicitly
+// labelled fast mode (precision=1) and is NOT used for parity.
+//
+// Warp roles (320 threads, 1 CTA/SM):
+//   warp 0      : weight loader -- one elected thread streams pre-packed, pre-split, pre-swizzled weight tiles
+//                 with 1-D bulk async copies (cp.async.bulk -> UBLKCP) completing on an mbarrier;
+//   warp 1      : TMEM allocator + MMA issuer -- one elected thread issues tcgen05.mma, commits to mbarriers;
+//   warps 2..9  : two producer groups (alternating k-blocks): coalesced 128-bit global loads of the activation
+//                 tile (8 lanes cover one pixel's 128 B), pre-op + hi/lo split in registers, swizzled 128-bit
+//                 shared stores of both halves, fence.proxy.async, mbarrier arrive; afterwards the same warps
+//                 run the epilogue: tcgen05.ld of the accumulator rows, activation, vectorised NHWC stores.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                 // fp32 elements per k-block = one 128-byte row
+constexpr int MAX_N = 128;
+constexpr int STAGES = 3;
+constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB (hi or lo)
+constexpr int NUM_THREADS = 320;
+constexpr int PRODUCER_THREADS = 128;       // per group
+constexpr int MAX_CIN_SMEM = 4096;          // pre-op scale/shift staged in smem
+
+struct ConvParams {
+    const float *x;          // NHWC source, pixel stride xs floats
+    long long xs;
+    int B, Hs, Ws;           // source dims (before the optional x2 up-sample)
+    int up;                  // 1: nearest x2 up-sample folded in (conv sees 2Hs x 2Ws)
+    int Cin;
+    int KH, KW, stride, pad, dil;
+    const float *wpack;      // packed weights (see pack kernel)
+    int n_tile, n_tiles, Cout;
+    const float *pre_scale;  // [Cin] or null
+    const float *pre_shift;  // [Cin] or null
+    int pre_relu;
+    float *out;              // NHWC, pixel stride os floats (may be a channel slice of a wider slab)
+    long long os;
+    int Hout, Wout;
+    int act;                 // 0 none, 1 ELU, 2 sigmoid
+    int precision;           // 0: 3xTF32 (parity), 1: 1xTF32 (fast, labelled)
+    int vec_ok;              // 16-byte aligned rows -> float4 loads
+    long long M;             // B*Hout*Wout
+    int KC;                  // ceil(Cin/32)
+    int KB;                  // KH*KW*KC k-blocks
+};
+
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------- weight packing
+// wpack layout: [n_tiles][KB][2 (hi,lo)][n_tile rows][32 floats], each row 128 B with the 16-byte chunk index
+// XOR-ed by (row & 7) -- exactly the shared-memory image of a K-major SWIZZLE_128B tile, so one contiguous bulk
+// copy per k-block lands it.  k-block order: tap-major, then 32-channel chunk.
+// transpose_flip=1 packs the dgrad operator: rows = ci, k = (flipped tap, co).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
+                                                           long long s_kh, long long s_kw, int Cout, int Cin, int KH,
+                                                           int KW, int transpose_flip, float *__restrict__ wpack,
+                                                           int n_tile, int n_tiles) {
+    const int Nrows = transpose_flip ? Cin : Cout;    // GEMM N
+    const int Kch = transpose_flip ? Cout : Cin;      // GEMM K channels per tap
+    const int KC = (Kch + 31) / 32;
+    const int KB = KH * KW * KC;
+    const long long total = (long long)n_tiles * KB * n_tile * 32;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(idx & 31);
+        long long t = idx >> 5;
+        const int n = (int)(t % n_tile);
+        t /= n_tile;
+        const int kb = (int)(t % KB);
+        const int nt = (int)(t / KB);
+        const int tap = kb / KC, kc = kb % KC;
+        const int row = nt * n_tile + n, ch = kc * 32 + kk;
+        float val = 0.f;
+        if (row < Nrows && ch < Kch) {
+            int kh = tap / KW, kw = tap % KW;
+            long long off;
+            if (transpose_flip) {
+                kh = KH - 1 - kh; kw = KW - 1 - kw;
+                off = (long long)ch * s_co + (long long)row * s_ci + kh * s_kh + kw * s_kw;
+            } else {
+                off = (long long)row * s_co + (long long)ch * s_ci + kh * s_kh + kw * s_kw;
+            }
+            val = w[off];
+        }
+        const float hi = rna_tf32(val);
+        const float lo = rna_tf32(val - hi);
+        const size_t tile = ((size_t)nt * KB + kb) * 2 * (size_t)n_tile * 32;
+        const size_t in_tile = (size_t)n * 32 + (size_t)(((kk >> 2) ^ (n & 7)) << 2) + (kk & 3);
+        wpack[tile + in_tile] = hi;
+        wpack[tile + (size_t)n_tile * 32 + in_tile] = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- main kernel
+struct SmemLayout {
+    // dynamic smem, 1024-byte aligned base:
+    //   [STAGES][A_hi 16K | A_lo 16K | B_hi n_tile*128 | B_lo n_tile*128]   (B region sized for MAX_N)
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * MAX_N * 128;   // 64 KB
+    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;                      // scale[MAX_CIN_SMEM], shift[...]
+    static constexpr int BAR_OFF = PRE_OFF + 2 * MAX_CIN_SMEM * 4;
+    static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+    float *s_scale = reinterpret_cast<float *>(sm + SmemLayout::PRE_OFF);
+    float *s_shift = s_scale + MAX_CIN_SMEM;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SmemLayout::BAR_OFF);
+    // bars: [0..S) full_a, [S..2S) full_b, [2S..3S) empty, [3S] accum_full; then the TMEM base address word
+    const uint32_t bar0 = base + SmemLayout::BAR_OFF;
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    const uint32_t accum_full = bar0 + 8u * (3 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, nt = blockIdx.y;
+    const int n_tile = p.n_tile;
+    const int KB = p.KB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_a(s), PRODUCER_THREADS);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (p.pre_scale) {
+        for (int c = threadIdx.x; c < p.KC * 32; c += NUM_THREADS) {
+            s_scale[c] = c < p.Cin ? p.pre_scale[c] : 0.f;
+            s_shift[c] = c < p.Cin ? p.pre_shift[c] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== weight loader =====================
+        if (lane == 0) {
+            const uint32_t bytes = 2u * (uint32_t)n_tile * 128u;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * bytes;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_arrive_expect_tx(full_b(s), bytes);
+                bulk_copy_g2s(base + s * SmemLayout::STAGE_BYTES + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
+                const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                const uint32_t b_lo = b_hi + n_tile * 128;
+                const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+                if (p.precision == 0) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
+                        umma_tf32(tmem_base, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(tmem_base, dah + 2 * k, dbl + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 8; ++k)
+                        umma_tf32(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                }
+                umma_commit(empty(s));       // frees the stage when these MMAs have read it
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // ===================== activation producers (2 groups x 4 warps) =====================
+        const int pt = threadIdx.x - 64;           // 0..255
+        const int grp = pt >> 7;                   // producer group: k-blocks kb == grp (mod 2)
+        const int t = pt & 127;
+        const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
+        const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7
+        const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
+        // per-row output pixel coordinates (fixed for the whole tile)
+        int oy[8], ox[8];
+        long long obase[8];                        // source offset of image b (floats); <0 => row beyond M
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
+            if (m < p.M) {
+                const int x = (int)(m % p.Wout);
+                const long long q = m / p.Wout;
+                const int y = (int)(q % p.Hout);
+                const int b = (int)(q / p.Hout);
+                oy[i] = y * p.stride - p.pad;
+                ox[i] = x * p.stride - p.pad;
+                obase[i] = (long long)b * p.Hs * p.Ws * p.xs;
+            } else {
+                oy[i] = ox[i] = 0;
+                obase[i] = -1;
+            }
+        }
+        const bool has_aff = p.pre_scale != nullptr;
+        for (int kb = grp; kb < KB; kb += 2) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            const int tap = kb / p.KC, kc = kb - tap * p.KC;
+            const int dy = (tap / p.KW) * p.dil, dx = (tap % p.KW) * p.dil;
+            const int c = kc * 32 + chunk * 4;     // first channel of this lane's chunk
+            // ---- issue all global loads of this k-block (8 x 16 B per thread)
+            F4 v[8];
+            bool inb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int yy = oy[i] + dy, xx = ox[i] + dx;
+                inb[i] = obase[i] >= 0 && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                v[i].v[0] = v[i].v[1] = v[i].v[2] = v[i].v[3] = 0.f;
+                if (inb[i]) {
+                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
+                    const float *src = p.x + obase[i] + ((long long)sy * p.Ws + sx) * p.xs + c;
+                    if (p.vec_ok && c + 3 < p.Cin) {
+                        const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+                        v[i].v[0] = q.x; v[i].v[1] = q.y; v[i].v[2] = q.z; v[i].v[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < p.Cin) v[i].v[e] = __ldg(src + e);
+                    }
+                }
+            }
+            // ---- wait for the stage to be free, then transform + split + swizzled stores
+            mbar_wait(empty(s), ph ^ 1);
+            uint8_t *a_hi = sm + s * SmemLayout::STAGE_BYTES;
+            uint8_t *a_lo = a_hi + A_TILE_BYTES;
+            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (has_aff) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { sc[e] = s_scale[c + e]; sh[e] = s_shift[c + e]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = r0 + 16 * i;
+                F4 hi, lo;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = v[i].v[e];
+                    if (has_aff) a = fmaf(a, sc[e], sh[e]);
+                    if (p.pre_relu) a = fmaxf(a, 0.f);
+                    if (!inb[i] || c + e >= p.Cin) a = 0.f;     // zero padding is applied after the pre-op
+                    const float h = rna_tf32(a);
+                    hi.v[e] = h;
+                    lo.v[e] = rna_tf32(a - h);
+                }
+                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+                *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
+                *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
+            }
+            fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(full_a(s));
+        }
+
+        // ===================== epilogue (same 8 warps) =====================
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const long long m = (long long)m_tile * BLOCK_M + row;
+        const int half = n_tile >> 1;                            // columns per producer group
+        const int col0 = grp * half;
+        float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
+        const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0) && ((n_tile & 3) == 0);
+        for (int cc = 0; cc < half; cc += 8) {
+            uint32_t r[8];
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cc), r);
+            tmem_ld_wait();
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float a = __uint_as_float(r[e]);
+                if (p.act == 1) a = a > 0.f ? a : expm1f(a);
+                else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
+                o[e] = a;
+            }
+            if (m < p.M) {
+                const int cbase = nt * n_tile + col0 + cc;       // absolute output channel
+#pragma unroll
+                for (int e4 = 0; e4 < 8; e4 += 4) {
+                    if (ovec && cbase + e4 + 3 < p.Cout) {
+                        *reinterpret_cast<float4 *>(orow + col0 + cc + e4) = make_float4(o[e4], o[e4 + 1], o[e4 + 2], o[e4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (cbase + e4 + e < p.Cout) orow[col0 + cc + e4 + e] = o[e4 + e];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- C ABI
+extern "C" int bts_conv_n_tile(int Cout) {
+    int n = (Cout + 15) / 16 * 16;
+    if (n > MAX_N) {
+        // split into equal tiles <= 128, multiples of 16
+        const int tiles = (n + MAX_N - 1) / MAX_N;
+        n = ((Cout + tiles - 1) / tiles + 15) / 16 * 16;
+    }
+    return n;
+}
+
+extern "C" long long bts_conv_packed_floats(int n_rows, int k_channels, int KH, int KW) {
+    const int n_tile = bts_conv_n_tile(n_rows);
+    const int n_tiles = (n_rows + n_tile - 1) / n_tile;
+    const int KC = (k_channels + 31) / 32;
+    return (long long)n_tiles * KH * KW * KC * 2 * n_tile * 32;
+}
+
+extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
+                                     int Cout, int Cin, int KH, int KW, int transpose_flip, float *wpack, void *stream) {
+    if (!w || !wpack || Cout < 1 || Cin < 1 || KH < 1 || KW < 1) return BTS_EINVAL;
+    if (!bts_aligned16(wpack)) return BTS_EALIGN;
+    const int rows = transpose_flip ? Cin : Cout;
+    const int n_tile = bts_conv_n_tile(rows);
+    const int n_tiles = (rows + n_tile - 1) / n_tile;
+    const long long total = bts_conv_packed_floats(rows, transpose_flip ? Cout : Cin, KH, KW) / 2;
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    pack_weights_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW,
+                                                                    transpose_flip, wpack, n_tile, n_tiles);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                            int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                            const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
+                            long long out_pixel_stride, int act, int precision, void *stream) {
+    if (!x || !wpack || !out || B < 0 || Hs < 1 || Ws < 1 || Cin < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 ||
+        pad < 0 || dil < 1)
+        return BTS_EINVAL;
+    if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BTS_EINVAL;
+    if (pre_scale && Cin > MAX_CIN_SMEM) return BTS_EINVAL;
+    if (act < 0 || act > 2 || precision < 0 || precision > 1) return BTS_EINVAL;
+    if (!bts_aligned16(wpack)) return BTS_EALIGN;
+    if (B == 0) return 0;
+    ConvParams p;
+    p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = upsample2 ? 1 : 0; p.Cin = Cin;
+    p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = dil;
+    p.wpack = wpack; p.Cout = Cout;
+    p.n_tile = bts_conv_n_tile(Cout);
+    p.n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
+    p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu ? 1 : 0;
+    p.out = out; p.os = out_pixel_stride; p.act = act; p.precision = precision;
+    const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
+    p.Hout = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    if (p.Hout < 1 || p.Wout < 1) return BTS_EINVAL;
+    p.M = (long long)B * p.Hout * p.Wout;
+    p.KC = (Cin + 31) / 32;
+    p.KB = KH * KW * p.KC;
+    p.vec_ok = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SmemLayout::TOTAL + 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    if (m_tiles > 0x7fffffffLL) return BTS_EINVAL;
+    dim3 grid((unsigned)m_tiles, (unsigned)p.n_tiles);
+    conv_tc_kernel<<<grid, NUM_THREADS, SmemLayout::TOTAL + 1024, (cudaStream_t)stream>>>(p);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}

@@ -103,21 +103,23 @@ __device__ __forceinline__ float lpg_den(float n1, float n2, float n3, float u, 
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int R, int LAYOUT>
+// FUSED = false: depth only.  FUSED = true: scaled = depth/max_depth (+ optional ds = scaled[::R/2, ::R/2]).
+template <int R, int LAYOUT, bool FUSED>
 __global__ void __launch_bounds__(256) lpg_fwd_vec(const PlaneSrc plane, float *__restrict__ depth,
                                                    float *__restrict__ scaled, float *__restrict__ ds,
-                                                   float max_depth, int S, int B, int h, int w) {
+                                                   float max_depth, int B, int h, int w) {
     constexpr int NP = (R == 2) ? 2 : 1;   // patches per lane
     constexpr int CPP = 4 / NP;            // columns per patch within the float4
-    const int W = w * R, H = h * R, Wq = W >> 2;
-    const long long total = (long long)B * h * Wq;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int S = (R >= 4) ? R / 2 : 1;
+    const unsigned W = w * R, H = h * R, Wq = W >> 2;
+    const unsigned total = (unsigned)B * h * Wq;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int xq = (int)(idx % Wq);
-    const long long t = idx / Wq;
-    const int i = (int)(t % h), b = (int)(t / h);
-    const int j0 = (R == 2) ? 2 * xq : (4 * xq) / R;
-    const int c0 = (R == 2) ? 0 : (4 * xq) % R;
+    const unsigned xq = idx % Wq;
+    const unsigned t = idx / Wq;
+    const unsigned i = t % h, b = t / h;
+    const unsigned j0 = (R == 2) ? 2 * xq : (4 * xq) / R;
+    const unsigned c0 = (R == 2) ? 0 : (4 * xq) % R;
 
     float n1u[4], n2[NP], n3[NP], n4[NP];
 #pragma unroll
@@ -139,22 +141,18 @@ __global__ void __launch_bounds__(256) lpg_fwd_vec(const PlaneSrc plane, float *
             d[c] = __fdiv_rn(n4[p], den);
         }
         const size_t off = row0 + (size_t)k * W;
-        if (depth) *reinterpret_cast<float4 *>(depth + off) = make_float4(d[0], d[1], d[2], d[3]);
-        if (scaled || ds) {
-            float s[4];
+        if (!FUSED) {
+            *reinterpret_cast<float4 *>(depth + off) = make_float4(d[0], d[1], d[2], d[3]);
+        } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) s[c] = __fdiv_rn(d[c], max_depth);
-            if (scaled) *reinterpret_cast<float4 *>(scaled + off) = make_float4(s[0], s[1], s[2], s[3]);
-            if (ds) {
-                const int y = i * R + k;
-                if (y % S == 0) {
-                    const int Ws = W / S, Hs = H / S;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int x = 4 * xq + c;
-                        if (x % S == 0) ds[((size_t)b * Hs + y / S) * Ws + x / S] = s[c];
-                    }
-                }
+            for (int c = 0; c < 4; ++c) d[c] = __fdiv_rn(d[c], max_depth);
+            *reinterpret_cast<float4 *>(scaled + off) = make_float4(d[0], d[1], d[2], d[3]);
+            if (R >= 4 && (k % S) == 0 && ds) {
+                // nearest down-sample by S (Q14): rows k = 0, S; columns 4*xq + c with c % S == 0
+                const unsigned Ws = W / S, Hs = H / S;
+                float *q = ds + ((size_t)b * Hs + (i * R + k) / S) * Ws + (4 * xq) / S;
+                if (S == 4) q[0] = d[0];
+                else { q[0] = d[0]; q[1] = d[2]; }
             }
         }
     }
@@ -184,85 +182,107 @@ __global__ void __launch_bounds__(256) lpg_fwd_generic(const PlaneSrc plane, flo
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// dY_total(y,x) = d_depth + (d_scaled + [y%S==0 && x%S==0] d_ds[y/S,x/S]) / max_depth
-template <int R, int LAYOUT>
+// FUSED = false: dY = d_depth.
+// FUSED = true : dY = (d_scaled + [y%S==0 && x%S==0] d_ds[y/S, x/S]) / max_depth with S = R/2 (d_ds optional).
+// Every global load of the tile is issued before the first use (R independent 16-byte loads per lane in flight);
+// per pixel: den (2 FADD), one MUFU reciprocal, q = dY/den, pp = dY/den^2, three running sums.  The u / v / n4
+// factors are pulled out of the pixel loop: column sums carry u, row sums carry v.
+template <int R, int LAYOUT, bool FUSED>
 __global__ void __launch_bounds__(256) lpg_bwd_vec(const float *__restrict__ d_depth, const float *__restrict__ d_scaled,
-                                                   const float *__restrict__ d_ds, float max_depth, int S,
+                                                   const float *__restrict__ d_ds, float max_depth,
                                                    const PlaneSrc plane, float *__restrict__ dplane,
                                                    int B, int h, int w, int tf_compat) {
     constexpr int NP = (R == 2) ? 2 : 1;
     constexpr int CPP = 4 / NP;
     constexpr int LPP = (R >= 4) ? R / 4 : 1;   // lanes that share one patch (r=8: 2)
-    const int W = w * R, H = h * R, Wq = W >> 2;
-    const long long total = (long long)B * h * Wq;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int S = (R >= 4) ? R / 2 : 1;
+    const unsigned W = w * R, H = h * R, Wq = W >> 2;
+    const unsigned total = (unsigned)B * h * Wq;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < total;            // inactive lanes still take part in the shuffle
-    const long long idc = active ? idx : 0;
-    const int xq = (int)(idc % Wq);
-    const long long t = idc / Wq;
-    const int i = (int)(t % h), b = (int)(t / h);
-    const int j0 = (R == 2) ? 2 * xq : (4 * xq) / R;
-    const int c0 = (R == 2) ? 0 : (4 * xq) % R;
+    const unsigned idc = active ? idx : 0;
+    const unsigned xq = idc % Wq;
+    const unsigned t = idc / Wq;
+    const unsigned i = t % h, b = t / h;
+    const unsigned j0 = (R == 2) ? 2 * xq : (4 * xq) / R;
+    const unsigned c0 = (R == 2) ? 0 : (4 * xq) % R;
 
     float g[NP][4];
 #pragma unroll
     for (int p = 0; p < NP; ++p) g[p][0] = g[p][1] = g[p][2] = g[p][3] = 0.f;
 
     if (active) {
+        const size_t row0 = ((size_t)b * H + (size_t)i * R) * W + 4 * (size_t)xq;
+        const float *src = FUSED ? d_scaled : d_depth;
+        float4 dy4[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) dy4[k] = __ldg(reinterpret_cast<const float4 *>(src + row0 + (size_t)k * W));
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;   // d_ds contributions: rows 0 and S; columns 0 (and 2)
+        if (FUSED && R >= 4 && d_ds) {
+            const unsigned Ws = W / S, Hs = H / S;
+            const float *q = d_ds + ((size_t)b * Hs + (i * R) / S) * Ws + (4 * xq) / S;
+            e0 = __ldg(q);
+            e2 = __ldg(q + Ws);
+            if (S == 2) { e1 = __ldg(q + 1); e3 = __ldg(q + Ws + 1); }
+        }
         float4 pl[NP];
 #pragma unroll
         for (int p = 0; p < NP; ++p) pl[p] = load_plane<LAYOUT>(plane, b, i, j0 + p, h, w, false);
-        const size_t row0 = ((size_t)b * H + (size_t)i * R) * W + 4 * (size_t)xq;
-        // issue every load of the tile first (R independent 16-byte loads per source in flight)
         float dy[R][4];
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const size_t off = row0 + (size_t)k * W;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            if (d_scaled) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(d_scaled + off));
-                a[0] = t4.x; a[1] = t4.y; a[2] = t4.z; a[3] = t4.w;
+        for (int k = 0; k < R; ++k) { dy[k][0] = dy4[k].x; dy[k][1] = dy4[k].y; dy[k][2] = dy4[k].z; dy[k][3] = dy4[k].w; }
+        if (FUSED) {
+            if (R >= 4) {
+                dy[0][0] += e0; dy[S][0] += e2;
+                if (S == 2) { dy[0][2] += e1; dy[S][2] += e3; }
             }
-            if (d_ds) {
-                const int y = i * R + k;
-                if (y % S == 0) {
-                    const int Ws = W / S, Hs = H / S;
-                    const float *q = d_ds + ((size_t)b * Hs + y / S) * Ws;
+            const float inv_md = 1.0f / max_depth;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int x = 4 * xq + c;
-                        if (x % S == 0) a[c] += __ldg(q + x / S);
-                    }
-                }
-            }
-            if (d_scaled || d_ds) {
+            for (int k = 0; k < R; ++k)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) a[c] = __fdiv_rn(a[c], max_depth);
-            }
-            if (d_depth) {
-                const float4 d = __ldg(reinterpret_cast<const float4 *>(d_depth + off));
-                a[0] += d.x; a[1] += d.y; a[2] += d.z; a[3] += d.w;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dy[k][c] = a[c];
+                for (int c = 0; c < 4; ++c) dy[k][c] *= inv_md;
         }
+        float n1u[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) n1u[c] = __fmul_rn(pl[c / CPP].x, grid_at<R>(c0 + (c % CPP)));
+        float colsum[4] = {0.f, 0.f, 0.f, 0.f};   // sum over rows of pp, per column
+        float vsum[NP], qsum[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) vsum[p] = qsum[p] = 0.f;
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const float v = grid_at<R>(k);
+            float rowsum[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) rowsum[p] = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int p = c / CPP;
-                const float u = grid_at<R>(c0 + (c % CPP));
-                const float den = lpg_den(pl[p].x, pl[p].y, pl[p].z, u, v);
-                const float inv = __frcp_rn(den);
+                const float den = __fadd_rn(__fadd_rn(n1u[c], __fmul_rn(pl[p].y, v)), pl[p].z);
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
                 const float q = dy[k][c] * inv;       // dY/den
-                float pp = q * inv;                   // dY/den^2
-                if (!tf_compat) pp *= pl[p].w;        // true gradient carries n4
-                g[p][0] -= pp * u;
-                g[p][1] -= pp * v;
-                g[p][2] -= pp;
-                g[p][3] += q;
+                const float pp = q * inv;             // dY/den^2
+                colsum[c] += pp;
+                rowsum[p] += pp;
+                qsum[p] += q;
             }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) vsum[p] = fmaf(v, rowsum[p], vsum[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float us = 0.f, ps = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPP; ++c) {
+                us = fmaf(grid_at<R>(c0 + c), colsum[p * CPP + c], us);
+                ps += colsum[p * CPP + c];
+            }
+            const float sc = tf_compat ? 1.0f : pl[p].w;   // true gradient carries n4
+            g[p][0] = -sc * us;
+            g[p][1] = -sc * vsum[p];
+            g[p][2] = -sc * ps;
+            g[p][3] = qsum[p];
         }
     }
     if (LPP > 1) {
@@ -323,15 +343,20 @@ bool fast_ok(int r, int w, int layout, const void *a, const void *b, const void 
 template <int LAYOUT>
 int launch_fwd(const PlaneSrc plane, float *depth, float *scaled, float *ds, float max_depth, int S, int B, int h,
                int w, int r, cudaStream_t st) {
-    if (fast_ok(r, w, LAYOUT, depth, scaled, nullptr, plane.p)) {
-        const long long total = (long long)B * h * (w * r / 4);
+    const long long total = (long long)B * h * (w * r / 4);
+    // vector kernels: depth only, or scaled (+ ds with stride r/2) only; everything else -> generic kernel
+    const bool plain = depth && !scaled && !ds;
+    const bool fused = !depth && scaled && (!ds || (r >= 4 && S == r / 2));
+    if (fast_ok(r, w, LAYOUT, depth, scaled, nullptr, plane.p) && (plain || fused) && total < 0x7fffffffLL) {
         const int grid = bts_ceil_div(total, 256);
-        if (r == 2) lpg_fwd_vec<2, LAYOUT><<<grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, S, B, h, w);
-        else if (r == 4) lpg_fwd_vec<4, LAYOUT><<<grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, S, B, h, w);
-        else lpg_fwd_vec<8, LAYOUT><<<grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, S, B, h, w);
+#define BTS_FWD(RR)                                                                                                \
+    if (plain) lpg_fwd_vec<RR, LAYOUT, false><<<grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, B, h, w); \
+    else lpg_fwd_vec<RR, LAYOUT, true><<<grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, B, h, w);
+        if (r == 2) { BTS_FWD(2) } else if (r == 4) { BTS_FWD(4) } else { BTS_FWD(8) }
+#undef BTS_FWD
     } else {
-        const long long total = (long long)B * h * r * w * r;
-        long long grid = (total + 255) / 256;
+        const long long npx = (long long)B * h * r * w * r;
+        long long grid = (npx + 255) / 256;
         const long long cap = (long long)bts_num_sms() * 16;
         if (grid > cap) grid = cap;
         lpg_fwd_generic<LAYOUT><<<(int)grid, 256, 0, st>>>(plane, depth, scaled, ds, max_depth, S, B, h, w, r);
@@ -343,15 +368,22 @@ int launch_fwd(const PlaneSrc plane, float *depth, float *scaled, float *ds, flo
 template <int LAYOUT>
 int launch_bwd(const float *d_depth, const float *d_scaled, const float *d_ds, float max_depth, int S,
                const PlaneSrc plane, float *dplane, int B, int h, int w, int r, int tfc, cudaStream_t st) {
-    if (fast_ok(r, w, LAYOUT, d_depth, d_scaled, LAYOUT == BTS_LAYOUT_NHWC ? (const void *)dplane : nullptr, plane.p)) {
-        const long long total = (long long)B * h * (w * r / 4);
+    const long long total = (long long)B * h * (w * r / 4);
+    const bool plain = d_depth && !d_scaled && !d_ds;
+    const bool fused = !d_depth && d_scaled && (!d_ds || (r >= 4 && S == r / 2));
+    if (fast_ok(r, w, LAYOUT, d_depth, d_scaled, LAYOUT == BTS_LAYOUT_NHWC ? (const void *)dplane : nullptr, plane.p) &&
+        (plain || fused) && total < 0x7fffffffLL) {
         const int grid = bts_ceil_div(total, 256);
-        if (r == 2) lpg_bwd_vec<2, LAYOUT><<<grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, S, plane, dplane, B, h, w, tfc);
-        else if (r == 4) lpg_bwd_vec<4, LAYOUT><<<grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, S, plane, dplane, B, h, w, tfc);
-        else lpg_bwd_vec<8, LAYOUT><<<grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, S, plane, dplane, B, h, w, tfc);
+#define BTS_BWD(RR)                                                                                              \
+    if (plain) lpg_bwd_vec<RR, LAYOUT, false><<<grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, plane,   \
+                                                                    dplane, B, h, w, tfc);                       \
+    else lpg_bwd_vec<RR, LAYOUT, true><<<grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, plane, dplane, \
+                                                             B, h, w, tfc);
+        if (r == 2) { BTS_BWD(2) } else if (r == 4) { BTS_BWD(4) } else { BTS_BWD(8) }
+#undef BTS_BWD
     } else {
-        const long long total = (long long)B * h * w;
-        long long grid = (total + 255) / 256;
+        const long long npatch = (long long)B * h * w;
+        long long grid = (npatch + 255) / 256;
         const long long cap = (long long)bts_num_sms() * 16;
         if (grid > cap) grid = cap;
         lpg_bwd_generic<LAYOUT><<<(int)grid, 256, 0, st>>>(d_depth, d_scaled, d_ds, max_depth, S, plane, dplane, B, h, w, r, tfc);
@@ -361,7 +393,8 @@ int launch_bwd(const float *d_depth, const float *d_scaled, const float *d_ds, f
 }
 
 int check_common(const void *plane, int B, int h, int w, int r, int layout) {
-    if (!plane || B < 0 || h < 0 || w < 0) return BTS_EINVAL;
+    if (B < 0 || h < 0 || w < 0) return BTS_EINVAL;
+    if (!plane && (long long)B * h * w != 0) return BTS_EINVAL;   // an empty tensor may legitimately be null
     if (r < 1 || (r > 1 && (r % 2) != 0)) return BTS_EINVAL;   // "Upratio should be multiple of 2 or 1" (.cc:36-44)
     if (layout != BTS_LAYOUT_NCHW && layout != BTS_LAYOUT_NHWC) return BTS_EINVAL;
     return 0;
@@ -373,6 +406,7 @@ extern "C" int bts_lpg_fwd_fused(const float *plane, float *depth, float *scaled
                                  int ds_stride, int B, int h, int w, int r, int layout, void *stream) {
     int rc = check_common(plane, B, h, w, r, layout);
     if (rc) return rc;
+    if ((long long)B * h * w == 0) return 0;   // empty input: nothing to do (TF op allocates an empty output)
     if (!depth && !scaled && !ds) return BTS_EINVAL;
     if ((scaled || ds) && !(max_depth > 0.f)) return BTS_EINVAL;
     if (ds && (ds_stride < 1 || (h * r) % ds_stride || (w * r) % ds_stride)) return BTS_EINVAL;
@@ -385,7 +419,7 @@ extern "C" int bts_lpg_fwd_fused(const float *plane, float *depth, float *scaled
 }
 
 extern "C" int bts_lpg_fwd(const float *plane, float *depth, int B, int h, int w, int r, int layout, void *stream) {
-    if (!depth) return BTS_EINVAL;
+    if (!depth && (long long)B * h * w != 0) return BTS_EINVAL;
     return bts_lpg_fwd_fused(plane, depth, nullptr, nullptr, 1.f, 1, B, h, w, r, layout, stream);
 }
 
@@ -394,6 +428,7 @@ extern "C" int bts_lpg_bwd_fused(const float *d_depth, const float *d_scaled, co
                                  int layout, int tf_compat, void *stream) {
     int rc = check_common(plane, B, h, w, r, layout);
     if (rc) return rc;
+    if ((long long)B * h * w == 0) return 0;
     if (!dplane || (!d_depth && !d_scaled && !d_ds)) return BTS_EINVAL;
     if ((d_scaled || d_ds) && !(max_depth > 0.f)) return BTS_EINVAL;
     if (d_ds && (ds_stride < 1 || (h * r) % ds_stride || (w * r) % ds_stride)) return BTS_EINVAL;
@@ -408,7 +443,7 @@ extern "C" int bts_lpg_bwd_fused(const float *d_depth, const float *d_scaled, co
 
 extern "C" int bts_lpg_bwd(const float *dy, const float *plane, float *dplane, int B, int h, int w, int r, int layout,
                            int tf_compat, void *stream) {
-    if (!dy) return BTS_EINVAL;
+    if (!dy && (long long)B * h * w != 0) return BTS_EINVAL;
     return bts_lpg_bwd_fused(dy, nullptr, nullptr, 1.f, 1, plane, dplane, B, h, w, r, layout, tf_compat, stream);
 }
 

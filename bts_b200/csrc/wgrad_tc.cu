@@ -1,0 +1,345 @@
+// Weight-gradient (wgrad) of the implicit-GEMM convolution on tcgen05 + TMEM, sm_100a, 3xTF32.
+//
+//   dW[co, ci, tap] = sum_p  dY[p, co] * pre(x[p (+) tap, ci])            (same pre / (+) as conv_tc.cu)
+//
+// GEMM view per (tap, split):  M = 128 input channels (TMEM lanes), N = n_tile output channels, K = output pixels.
+// Both operands live in memory as [pixel][channel] (NHWC), i.e. the reduction index is the slow one, so both shared
+// memory tiles are "MN-major": [32-channel chunk][32 pixel rows][128 B] in the SWIZZLE_128B_BASE32B pattern (the only
+// one the tensor core accepts for MN-major TF32), UMMA descriptors with a_major = b_major = MN, LBO = chunk stride.
+// grid = (ceil(Cin/128), n_tiles(Cout), taps * splitK); each CTA reduces its pixel range into an fp32 TMEM tile and
+// writes a partial; a second, deterministic kernel sums the splitK partials into the (Cout,Cin,KH,KW)-strided gradient.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int BLOCK_CI = 128;
+constexpr int BLOCK_KP = 32;                 // pixels per k-block
+constexpr int MAX_N = 128;
+constexpr int STAGES = 3;
+constexpr int CHUNK_BYTES = BLOCK_KP * 128;  // one 32-channel chunk of a k-block: 4 KB
+constexpr int A_BYTES = 4 * CHUNK_BYTES;     // 16 KB (hi or lo)
+constexpr int NUM_THREADS = 320;
+constexpr int MAX_CIN_SMEM = 4096;
+
+struct WgradParams {
+    const float *x; long long xs;
+    int B, Hs, Ws, up, Cin;
+    int KH, KW, stride, pad, dil;
+    const float *pre_scale, *pre_shift; int pre_relu;
+    const float *dy; long long dys;
+    int Cout, Hout, Wout;
+    int n_tile;
+    float *part;             // [splitK][taps][Cin][Cout]
+    int splitK, kb_per_split, KBp;
+    int M;
+    int x_vec, dy_vec, precision;
+};
+
+struct Smem {
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * MAX_N * 128;   // 64 KB
+    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = PRE_OFF + 2 * MAX_CIN_SMEM * 4;
+    static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+    float *s_scale = reinterpret_cast<float *>(sm + Smem::PRE_OFF);
+    float *s_shift = s_scale + MAX_CIN_SMEM;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + Smem::BAR_OFF);
+    const uint32_t bar0 = base + Smem::BAR_OFF;
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t accum_full = bar0 + 8u * (2 * STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci_tile = blockIdx.x, nt = blockIdx.y;
+    const int tap = blockIdx.z / p.splitK, split = blockIdx.z % p.splitK;
+    const int n_tile = p.n_tile;
+    const int kb0 = split * p.kb_per_split;
+    int kb1 = kb0 + p.kb_per_split;
+    if (kb1 > p.KBp) kb1 = p.KBp;
+    const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), 128);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (p.pre_scale) {
+        for (int c = threadIdx.x; c < BLOCK_CI; c += NUM_THREADS) {
+            const int ch = ci_tile * BLOCK_CI + c;
+            s_scale[c] = ch < p.Cin ? p.pre_scale[ch] : 0.f;
+            s_shift[c] = ch < p.Cin ? p.pre_shift[ch] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = base + s * Smem::STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + MAX_N * 128;
+#pragma unroll
+                for (int kg = 0; kg < BLOCK_KP / 8; ++kg) {
+                    const uint64_t dah = make_desc_mn(a_hi + kg * 1024, CHUNK_BYTES), dal = make_desc_mn(a_lo + kg * 1024, CHUNK_BYTES);
+                    const uint64_t dbh = make_desc_mn(b_hi + kg * 1024, CHUNK_BYTES), dbl = make_desc_mn(b_lo + kg * 1024, CHUNK_BYTES);
+                    if (p.precision == 0) {
+                        umma_tf32(tmem_base, dal, dbh, idesc, (it | kg) != 0);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    } else {
+                        umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
+                    }
+                }
+                umma_commit(empty(s));
+            }
+            umma_commit(accum_full);
+        }
+    } else if (warp >= 2) {
+        const int pt = threadIdx.x - 64;
+        const int grp = pt >> 7;
+        const int t = pt & 127;
+        const int unit = t & 7;                    // 16-byte unit of the 128-byte row
+        const int r0 = t >> 3;                     // pixel rows r0, r0 + 16 of the 32-pixel k-block
+        const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
+        const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
+        const bool has_aff = p.pre_scale != nullptr;
+        const int nchunk_b = (n_tile + 31) >> 5;
+        for (int it = grp; it < nkb; it += 2) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const int kb = kb0 + it;
+            // ---- the two pixel rows of this thread
+            const float *xsrc[2];
+            const float *dsrc[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = kb * BLOCK_KP + r0 + 16 * h;
+                xsrc[h] = nullptr;
+                dsrc[h] = nullptr;
+                if (m < p.M) {
+                    const int x = m % p.Wout;
+                    const int q = m / p.Wout;
+                    const int y = q % p.Hout;
+                    const int b = q / p.Hout;
+                    dsrc[h] = p.dy + (long long)m * p.dys;
+                    const int yy = y * p.stride + dyo, xx = x * p.stride + dxo;
+                    if ((unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win) {
+                        const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
+                        xsrc[h] = p.x + (((long long)b * p.Hs + sy) * p.Ws + sx) * p.xs;
+                    }
+                }
+            }
+            // ---- global loads: A (x, 4 chunks x 2 rows) and B (dy, nchunk_b chunks x 2 rows)
+            F4 va[8], vb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int h = i & 1, chunk = i >> 1;
+                const int c = ci_tile * BLOCK_CI + chunk * 32 + unit * 4;
+                va[i].v[0] = va[i].v[1] = va[i].v[2] = va[i].v[3] = 0.f;
+                if (xsrc[h]) {
+                    if (p.x_vec && c + 3 < p.Cin) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(xsrc[h] + c));
+                        va[i].v[0] = q4.x; va[i].v[1] = q4.y; va[i].v[2] = q4.z; va[i].v[3] = q4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < p.Cin) va[i].v[e] = __ldg(xsrc[h] + c + e);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int h = i & 1, chunk = i >> 1;
+                const int c = nt * n_tile + chunk * 32 + unit * 4;
+                vb[i].v[0] = vb[i].v[1] = vb[i].v[2] = vb[i].v[3] = 0.f;
+                if (chunk < nchunk_b && dsrc[h]) {
+                    if (p.dy_vec && c + 3 < p.Cout) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(dsrc[h] + c));
+                        vb[i].v[0] = q4.x; vb[i].v[1] = q4.y; vb[i].v[2] = q4.z; vb[i].v[3] = q4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < p.Cout) vb[i].v[e] = __ldg(dsrc[h] + c + e);
+                    }
+                }
+            }
+            mbar_wait(empty(s), ph ^ 1);
+            uint8_t *a_hi = sm + s * Smem::STAGE_BYTES, *a_lo = a_hi + A_BYTES;
+            uint8_t *b_hi = a_hi + 2 * A_BYTES, *b_lo = b_hi + MAX_N * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int h = i & 1, chunk = i >> 1;
+                const int row = r0 + 16 * h;
+                const uint32_t off = (uint32_t)chunk * CHUNK_BYTES + mn_swizzle_off(row, unit);
+                const int cl = chunk * 32 + unit * 4;             // channel within the 128-channel tile
+                F4 hi, lo;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = va[i].v[e];
+                    if (has_aff) a = fmaf(a, s_scale[cl + e], s_shift[cl + e]);
+                    if (p.pre_relu) a = fmaxf(a, 0.f);
+                    if (!xsrc[h] || ci_tile * BLOCK_CI + cl + e >= p.Cin) a = 0.f;
+                    const float hh = rna_tf32(a);
+                    hi.v[e] = hh;
+                    lo.v[e] = rna_tf32(a - hh);
+                }
+                *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
+                *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
+                if (chunk < nchunk_b) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a = vb[i].v[e];
+                        const float hh = rna_tf32(a);
+                        hi.v[e] = hh;
+                        lo.v[e] = rna_tf32(a - hh);
+                    }
+                    *reinterpret_cast<float4 *>(b_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
+                    *reinterpret_cast<float4 *>(b_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full(s));
+        }
+
+        // ---- epilogue: TMEM lane = input channel, columns = output channels
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int ci = ci_tile * BLOCK_CI + q * 32 + lane;
+        const int half = n_tile >> 1;
+        const int col0 = grp * half;
+        const int taps = p.KH * p.KW;
+        float *prow = p.part + (((long long)split * taps + tap) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + (long long)nt * n_tile;
+        const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0);
+        for (int cc = 0; cc < half; cc += 8) {
+            uint32_t r[8];
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cc), r);
+            tmem_ld_wait();
+            if (ci < p.Cin) {
+                const int cbase = nt * n_tile + col0 + cc;
+#pragma unroll
+                for (int e4 = 0; e4 < 8; e4 += 4) {
+                    if (ovec && cbase + e4 + 3 < p.Cout) {
+                        *reinterpret_cast<float4 *>(prow + col0 + cc + e4) =
+                            make_float4(nkb ? __uint_as_float(r[e4]) : 0.f, nkb ? __uint_as_float(r[e4 + 1]) : 0.f,
+                                        nkb ? __uint_as_float(r[e4 + 2]) : 0.f, nkb ? __uint_as_float(r[e4 + 3]) : 0.f);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (cbase + e4 + e < p.Cout) prow[col0 + cc + e4 + e] = nkb ? __uint_as_float(r[e4 + e]) : 0.f;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// dW[co,ci,kh,kw] (arbitrary strides) = sum_split part[split][tap][ci][co]; fixed summation order -> deterministic
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ part, int splitK, int taps, int Cin,
+                                                           int Cout, int KW, float *__restrict__ dw, long long s_co,
+                                                           long long s_ci, long long s_kh, long long s_kw) {
+    const long long per = (long long)taps * Cin * Cout;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < per;
+         idx += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < splitK; ++s) acc += part[(long long)s * per + idx];
+        const int co = (int)(idx % Cout);
+        const long long t = idx / Cout;
+        const int ci = (int)(t % Cin);
+        const int tap = (int)(t / Cin);
+        dw[co * s_co + ci * s_ci + (tap / KW) * s_kh + (tap % KW) * s_kw] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" int bts_conv_n_tile(int Cout);
+
+extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int *splitK_out,
+                                   long long *workspace_floats) {
+    if (!splitK_out || !workspace_floats || B < 1 || Hout < 1 || Wout < 1 || Cin < 1 || Cout < 1) return BTS_EINVAL;
+    const long long M = (long long)B * Hout * Wout;
+    const long long KBp = (M + BLOCK_KP - 1) / BLOCK_KP;
+    const int n_tile = bts_conv_n_tile(Cout);
+    const long long tiles = (long long)((Cin + BLOCK_CI - 1) / BLOCK_CI) * ((Cout + n_tile - 1) / n_tile) * KH * KW;
+    const int sms = bts_num_sms();
+    long long split = (2LL * sms + tiles - 1) / tiles;        // aim at ~2 waves of CTAs
+    if (split < 1) split = 1;
+    const long long max_split = (KBp + 15) / 16;              // at least 16 k-blocks (512 px) per CTA
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    if (split > 64) split = 64;
+    *splitK_out = (int)split;
+    *workspace_floats = split * KH * KW * (long long)Cin * Cout;
+    return 0;
+}
+
+extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                              int KH, int KW, int stride, int pad, int dil, const float *pre_scale,
+                              const float *pre_shift, int pre_relu, const float *dy, long long dy_pixel_stride, int Cout,
+                              float *workspace, int splitK, float *dw, long long s_co, long long s_ci, long long s_kh,
+                              long long s_kw, int precision, void *stream) {
+    if (!x || !dy || !workspace || !dw || B < 1 || Hs < 1 || Ws < 1 || Cin < 1 || Cout < 1 || KH < 1 || KW < 1 ||
+        stride < 1 || pad < 0 || dil < 1 || splitK < 1)
+        return BTS_EINVAL;
+    if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BTS_EINVAL;
+    WgradParams p;
+    p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = upsample2 ? 1 : 0; p.Cin = Cin;
+    p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = dil;
+    p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu ? 1 : 0;
+    p.dy = dy; p.dys = dy_pixel_stride; p.Cout = Cout;
+    const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
+    p.Hout = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    const long long M = (long long)B * p.Hout * p.Wout;
+    if (p.Hout < 1 || p.Wout < 1 || M > 0x7ffffff0LL) return BTS_EINVAL;
+    p.M = (int)M;
+    p.n_tile = bts_conv_n_tile(Cout);
+    p.part = workspace; p.splitK = splitK;
+    p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
+    p.kb_per_split = (p.KBp + splitK - 1) / splitK;
+    p.x_vec = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
+    p.dy_vec = bts_aligned16(dy) && (dy_pixel_stride % 4 == 0);
+    p.precision = precision;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL + 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int taps = KH * KW;
+    dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.n_tile - 1) / p.n_tile, taps * splitK);
+    if (grid.z > 65535) return BTS_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    wgrad_tc_kernel<<<grid, NUM_THREADS, Smem::TOTAL + 1024, st>>>(p);
+    BTS_LAUNCH_CHECK();
+    const long long per = (long long)taps * Cin * Cout;
+    long long g = (per + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (g > cap) g = cap;
+    wgrad_reduce_kernel<<<(int)g, 256, 0, st>>>(workspace, splitK, taps, Cin, Cout, KW, dw, s_co, s_ci, s_kh, s_kw);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}

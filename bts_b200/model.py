@@ -9,6 +9,7 @@ bts_test.py import this as `bts` unchanged.  The arithmetic underneath is ours:
 Reference lines are cited per class.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -45,9 +46,37 @@ class silog_loss(nn.Module):
         return ops.silog(depth_est, depth_gt, mask, self.variance_focus)
 
 
+def conv_backend():
+    """BTS_B200_CONV = tc (tcgen05 implicit-GEMM engine, bts_b200/csrc/conv_tc.cu) | cudnn (library scaffold)."""
+    return os.environ.get("BTS_B200_CONV", "tc")
+
+
+class Conv2dTC(nn.Conv2d):
+    """nn.Conv2d whose forward/dgrad run on the tcgen05 engine.  It stays an nn.Conv2d subclass so that
+    weights_init_xavier (bts_main.py:338), state_dict keys and optimizer groups behave exactly as in the reference."""
+
+    def forward(self, x):
+        if (conv_backend() == "tc" and x.is_cuda and x.dtype == torch.float32 and self.groups == 1
+                and self.bias is None and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
+                and self.dilation[0] == self.dilation[1] and self.kernel_size[0] == self.kernel_size[1]
+                and isinstance(self.padding, tuple) and self.padding_mode == "zeros"):
+            from . import conv
+            return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0])
+        return super().forward(x)
+
+
+def adopt_convs(module):
+    """Re-class every eligible nn.Conv2d of a (torchvision) module tree to Conv2dTC in place -- parameter names,
+    shapes and init are untouched."""
+    for m in module.modules():
+        if type(m) is nn.Conv2d:
+            m.__class__ = Conv2dTC
+    return module
+
+
 def _conv(cin, cout, k, dilation=1):
     pad = dilation * (k // 2)
-    return nn.Conv2d(cin, cout, k, 1, pad, dilation=dilation, bias=False)
+    return Conv2dTC(cin, cout, k, 1, pad, dilation=dilation, bias=False)
 
 
 class atrous_conv(nn.Sequential):
@@ -248,7 +277,7 @@ class encoder(nn.Module):
             return
         ctor, feats, names, ch = _ENCODERS[params.encoder]
         m = _load_backbone(ctor, getattr(params, "pretrained", None))
-        self.base_model = m.features if feats else m
+        self.base_model = adopt_convs(m.features if feats else m)
         self.feat_names = names
         self.feat_out_channels = ch
         if params.encoder == "mobilenetv2_bts":
@@ -278,4 +307,6 @@ class BtsModel(nn.Module):
         self.decoder = bts(params, self.encoder.feat_out_channels, params.bts_size)
 
     def forward(self, x, focal):
+        if x.is_cuda and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)      # NHWC in memory for the whole path
         return self.decoder(self.encoder(x), focal)

@@ -86,6 +86,40 @@ int bts_plane_head_fwd(const float *c3, float *plane_out, float *scaled, float *
 int bts_plane_head_bwd(const float *d_scaled, const float *d_ds, const float *c3, float *dc3,
                        float max_depth, int ds_stride, int B, int h, int w, int r, void *stream);
 
+/* ---- tcgen05 implicit-GEMM convolution (pytorch/bts.py:51-80,153-194; torchvision dense/bottleneck layers) ----
+ * NHWC activations, fp32 in / fp32 out, parity-grade 3xTF32 on the 5th-gen tensor cores (precision=0) or
+ * single-pass TF32 (precision=1, labelled fast mode, not parity).
+ *   out[p,co] = act( sum_{tap,ci} pre(x[p (+) tap, ci]) * w[co,ci,tap] )
+ *   pre : x*pre_scale[ci]+pre_shift[ci] (folded BatchNorm; both NULL to skip), then ReLU if pre_relu;
+ *         zero padding is applied after pre.  upsample2=1 folds a nearest x2 up-sample of the source in.
+ *   act : 0 none, 1 ELU, 2 sigmoid.
+ * x: source (B,Hs,Ws,*) with x_pixel_stride floats between pixels (a channel slice of a wider slab is fine);
+ * out likewise with out_pixel_stride.  Weights must first be packed (split hi/lo, K-major, 128B-swizzled tiles):
+ *   bts_conv_packed_floats(n_rows, k_channels, KH, KW) -> number of floats of the packed buffer
+ *   bts_conv_pack_weights(w, strides of (co,ci,kh,kw) in floats, ..., transpose_flip, wpack)
+ *       transpose_flip=0: forward operator (rows = Cout);  1: dgrad operator (rows = Cin, taps flipped) so that
+ *       dX = bts_conv_fwd(dY, wpack_T, Cin<->Cout swapped, pad' = dil*(K-1) - pad).
+ *   bts_conv_n_tile(Cout) -> the N tile the engine uses for that many output channels. */
+int bts_conv_n_tile(int Cout);
+long long bts_conv_packed_floats(int n_rows, int k_channels, int KH, int KW);
+int bts_conv_pack_weights(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
+                          int Cout, int Cin, int KH, int KW, int transpose_flip, float *wpack, void *stream);
+int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                 int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                 const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
+                 long long out_pixel_stride, int act, int precision, void *stream);
+
+/* wgrad on the same engine: dW[co,ci,tap] = sum_p dY[p,co] * pre(x[p (+) tap, ci]), MN-major tcgen05 operands,
+ * split-K partials in `workspace` reduced deterministically into dw (strides in floats).
+ *   bts_conv_wgrad_plan(...) -> splitK and the workspace size (floats) the call needs. */
+int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int *splitK_out,
+                        long long *workspace_floats);
+int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                   int KH, int KW, int stride, int pad, int dil, const float *pre_scale, const float *pre_shift,
+                   int pre_relu, const float *dy, long long dy_pixel_stride, int Cout, float *workspace, int splitK,
+                   float *dw, long long s_co, long long s_ci, long long s_kh, long long s_kw, int precision,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ from conftest import ROOT
 def _header_symbols():
     txt = open(os.path.join(ROOT, "include", "bts_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(bts_\w+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(bts_\w+)\s*\(", txt)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():

