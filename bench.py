@@ -297,7 +297,7 @@ def run_ours(args):
         x = himg.to(dev, non_blocking=True)
         f = hfocal.to(dev, non_blocking=True)
         g = hgt.to(dev, non_blocking=True)
-        return float(step(i, x, f, g))           # D2H read of the loss every step (bts_main.py:463)
+        return float(step(i, x, f, g).detach())  # D2H read of the loss every step (bts_main.py:463)
 
     ms_e, _, _ = timed(e2e_step, K, 1)
     h2d = himg.numel() * 4 + hfocal.numel() * 8 + hgt.numel() * 4

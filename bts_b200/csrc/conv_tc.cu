@@ -213,57 +213,85 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7
         const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
-        // per-row output pixel coordinates (fixed for the whole tile)
+        const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
+        // per-row output pixel origin in input coordinates (fixed for the whole tile) and 32-bit element offsets
         int oy[8], ox[8];
-        long long obase[8];                        // source offset of image b (floats); <0 => row beyond M
+        int rbase[8];                              // element offset of image b (row-valid) or -1 (row beyond M)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
             if (m < p.M) {
                 const int x = (int)(m % p.Wout);
-                const long long q = m / p.Wout;
-                const int y = (int)(q % p.Hout);
-                const int b = (int)(q / p.Hout);
+                const int q = (int)(m / p.Wout);
+                const int y = q % p.Hout;
+                const int b = q / p.Hout;
                 oy[i] = y * p.stride - p.pad;
                 ox[i] = x * p.stride - p.pad;
-                obase[i] = (long long)b * p.Hs * p.Ws * p.xs;
+                rbase[i] = b * p.Hs * p.Ws * xs;
             } else {
-                oy[i] = ox[i] = 0;
-                obase[i] = -1;
+                oy[i] = ox[i] = -0x40000000;       // never in bounds
+                rbase[i] = 0;
             }
         }
         const bool has_aff = p.pre_scale != nullptr;
-        for (int kb = grp; kb < KB; kb += 2) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
+        const float *__restrict__ xg = p.x;
+        const uint32_t swz = (uint32_t)(chunk << 4);
+        uint32_t roff[8];                          // swizzled byte offset of (row, chunk) inside a tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = r0 + 16 * i;
+            roff[i] = (uint32_t)row * 128u + (swz ^ (uint32_t)((row & 7) << 4));
+        }
+        // ---- load phase: this lane's 8 x 16-byte global loads of one k-block, branch-free (out-of-image / out-of-
+        //      range lanes read element 0 -- always valid -- and are zeroed in the store phase)
+        auto load_kb = [&](int kb, F4(&v)[8], uint32_t &mask) {
             const int tap = kb / p.KC, kc = kb - tap * p.KC;
-            const int dy = (tap / p.KW) * p.dil, dx = (tap % p.KW) * p.dil;
-            const int c = kc * 32 + chunk * 4;     // first channel of this lane's chunk
-            // ---- issue all global loads of this k-block (8 x 16 B per thread)
-            F4 v[8];
-            bool inb[8];
+            const int ky = tap / p.KW;
+            const int dy = ky * p.dil, dx = (tap - ky * p.KW) * p.dil;
+            const int c = kc * 32 + chunk * 4;     // first channel of this lane's 16-byte unit
+            const bool cany = c < p.Cin;
+            const bool cfull = c + 3 < p.Cin;
+            uint32_t mk = 0;
+            if (p.vec_ok && (cfull || !cany)) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int yy = oy[i] + dy, xx = ox[i] + dx;
-                inb[i] = obase[i] >= 0 && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                v[i].v[0] = v[i].v[1] = v[i].v[2] = v[i].v[3] = 0.f;
-                if (inb[i]) {
+                for (int i = 0; i < 8; ++i) {
+                    const int yy = oy[i] + dy, xx = ox[i] + dx;
+                    const bool ok = cany && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
                     const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
-                    const float *src = p.x + obase[i] + ((long long)sy * p.Ws + sx) * p.xs + c;
-                    if (p.vec_ok && c + 3 < p.Cin) {
-                        const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
-                        v[i].v[0] = q.x; v[i].v[1] = q.y; v[i].v[2] = q.z; v[i].v[3] = q.w;
-                    } else {
+                    const int off = ok ? rbase[i] + (sy * p.Ws + sx) * xs + c : 0;
+                    mk |= (ok ? 1u : 0u) << i;
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(xg + off));
+                    v[i].v[0] = q.x; v[i].v[1] = q.y; v[i].v[2] = q.z; v[i].v[3] = q.w;
+                }
+            } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < p.Cin) v[i].v[e] = __ldg(src + e);
+                for (int i = 0; i < 8; ++i) {
+                    const int yy = oy[i] + dy, xx = ox[i] + dx;
+                    const bool ok = cany && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
+                    const int off = ok ? rbase[i] + (sy * p.Ws + sx) * xs + c : 0;
+                    mk |= (ok ? 1u : 0u) << i;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool eok = ok && (c + e < p.Cin);
+                        const float q = __ldg(xg + (eok ? off + e : 0));
+                        v[i].v[e] = eok ? q : 0.f;
                     }
                 }
             }
-            // ---- wait for the stage to be free, then transform + split + swizzled stores
+            mask = mk;
+        };
+        // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
+        //      hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is
+        //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
+        auto store_kb = [&](int kb, F4(&v)[8], uint32_t mask) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            const int kc = kb % p.KC;
+            const int c = kc * 32 + chunk * 4;
             mbar_wait(empty(s), ph ^ 1);
-            uint8_t *a_hi = sm + s * SmemLayout::STAGE_BYTES;
-            uint8_t *a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
+            const uint32_t a_lo = a_hi + A_TILE_BYTES;
             float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
             if (has_aff) {
 #pragma unroll
@@ -271,24 +299,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int row = r0 + 16 * i;
-                F4 hi, lo;
+                const bool ok = (mask >> i) & 1u;
+                float hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float a = v[i].v[e];
-                    if (has_aff) a = fmaf(a, sc[e], sh[e]);
+                    if (has_aff) a = fmaf(a, sc[e], sh[e]);     // scale/shift are 0 beyond Cin
                     if (p.pre_relu) a = fmaxf(a, 0.f);
-                    if (!inb[i] || c + e >= p.Cin) a = 0.f;     // zero padding is applied after the pre-op
-                    const float h = rna_tf32(a);
-                    hi.v[e] = h;
-                    lo.v[e] = rna_tf32(a - h);
+                    a = ok ? a : 0.f;                           // zero padding is applied after the pre-op
+                    const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+                    hi[e] = h;
+                    lo[e] = a - h;
                 }
-                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-                *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
-                *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
+                st_shared_v4(a_hi + roff[i], hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + roff[i], lo[0], lo[1], lo[2], lo[3]);
             }
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(full_a(s));
+        };
+        // ---- software pipeline: the loads of this group's NEXT k-block are in flight while the current one is
+        //      transformed and stored (register ping-pong), so L2 latency hides behind a full k-block of work
+        {
+            F4 va[8], vb[8];
+            uint32_t ma = 0, mb = 0;
+            int kb = grp;
+            if (kb < KB) load_kb(kb, va, ma);
+            for (; kb < KB; kb += 4) {
+                const bool more = kb + 2 < KB;
+                if (more) load_kb(kb + 2, vb, mb);
+                store_kb(kb, va, ma);
+                if (more) {
+                    if (kb + 4 < KB) load_kb(kb + 4, va, ma);
+                    store_kb(kb + 2, vb, mb);
+                }
+            }
         }
 
         // ===================== epilogue (same 8 warps) =====================
@@ -382,6 +426,7 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     if (act < 0 || act > 2 || precision < 0 || precision > 1) return BTS_EINVAL;
     if (!bts_aligned16(wpack)) return BTS_EALIGN;
     if (B == 0) return 0;
+    if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;   // 32-bit element offsets
     ConvParams p;
     p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = upsample2 ? 1 : 0; p.Cin = Cin;
     p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = dil;

@@ -95,5 +95,9 @@ __device__ __forceinline__ float rna_tf32(float x) {
 
 struct __align__(16) F4 { float v[4]; };
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 
 }  // namespace tc

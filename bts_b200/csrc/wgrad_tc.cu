@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full(s), 128);
+            mbar_init(full(s), 256);      // both producer groups (x tile + dY tile) arrive
             mbar_init(empty(s), 1);
         }
         mbar_init(accum_full, 1);
@@ -115,109 +115,121 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         }
     } else if (warp >= 2) {
         const int pt = threadIdx.x - 64;
-        const int grp = pt >> 7;
+        const int grp = pt >> 7;                   // group 0 produces the x (A) tiles, group 1 the dY (B) tiles
         const int t = pt & 127;
         const int unit = t & 7;                    // 16-byte unit of the 128-byte row
         const int r0 = t >> 3;                     // pixel rows r0, r0 + 16 of the 32-pixel k-block
         const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
         const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
         const bool has_aff = p.pre_scale != nullptr;
-        const int nchunk_b = (n_tile + 31) >> 5;
-        for (int it = grp; it < nkb; it += 2) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
+        const int nchunk = grp == 0 ? 4 : ((n_tile + 31) >> 5);
+        const int cbase = grp == 0 ? ci_tile * BLOCK_CI : nt * n_tile;     // first channel of this tile
+        const int cmax = grp == 0 ? p.Cin : p.Cout;
+        const float *__restrict__ src = grp == 0 ? p.x : p.dy;
+        const bool vec = grp == 0 ? p.x_vec : p.dy_vec;
+        const int xs = (int)p.xs, dys = (int)p.dys;
+        const uint32_t tile_off = grp == 0 ? 0u : (uint32_t)(2 * A_BYTES);
+        const uint32_t lo_off = grp == 0 ? (uint32_t)A_BYTES : (uint32_t)(MAX_N * 128);
+        uint32_t roff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) roff[i] = (uint32_t)(i >> 1) * CHUNK_BYTES + mn_swizzle_off(r0 + 16 * (i & 1), unit);
+        float sc[4][4], sh[4][4];                  // per chunk, this lane's 4 channels (group 0 only)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sc[ch][e] = (has_aff && grp == 0) ? s_scale[ch * 32 + unit * 4 + e] : 1.f;
+                sh[ch][e] = (has_aff && grp == 0) ? s_shift[ch * 32 + unit * 4 + e] : 0.f;
+            }
+        auto load_kb = [&](int it, F4(&v)[8], uint32_t &mask) {
             const int kb = kb0 + it;
-            // ---- the two pixel rows of this thread
-            const float *xsrc[2];
-            const float *dsrc[2];
+            int off[2];
+            bool ok[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int m = kb * BLOCK_KP + r0 + 16 * h;
-                xsrc[h] = nullptr;
-                dsrc[h] = nullptr;
-                if (m < p.M) {
-                    const int x = m % p.Wout;
-                    const int q = m / p.Wout;
+                ok[h] = m < p.M;
+                off[h] = 0;
+                if (grp == 0) {
+                    const int mm = ok[h] ? m : 0;
+                    const int x = mm % p.Wout;
+                    const int q = mm / p.Wout;
                     const int y = q % p.Hout;
                     const int b = q / p.Hout;
-                    dsrc[h] = p.dy + (long long)m * p.dys;
                     const int yy = y * p.stride + dyo, xx = x * p.stride + dxo;
-                    if ((unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win) {
-                        const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
-                        xsrc[h] = p.x + (((long long)b * p.Hs + sy) * p.Ws + sx) * p.xs;
-                    }
+                    ok[h] = ok[h] && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
+                    if (ok[h]) off[h] = ((b * p.Hs + sy) * p.Ws + sx) * xs;
+                } else if (ok[h]) {
+                    off[h] = m * dys;
                 }
             }
-            // ---- global loads: A (x, 4 chunks x 2 rows) and B (dy, nchunk_b chunks x 2 rows)
-            F4 va[8], vb[8];
+            uint32_t mk = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int h = i & 1, chunk = i >> 1;
-                const int c = ci_tile * BLOCK_CI + chunk * 32 + unit * 4;
-                va[i].v[0] = va[i].v[1] = va[i].v[2] = va[i].v[3] = 0.f;
-                if (xsrc[h]) {
-                    if (p.x_vec && c + 3 < p.Cin) {
-                        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(xsrc[h] + c));
-                        va[i].v[0] = q4.x; va[i].v[1] = q4.y; va[i].v[2] = q4.z; va[i].v[3] = q4.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < p.Cin) va[i].v[e] = __ldg(xsrc[h] + c + e);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int h = i & 1, chunk = i >> 1;
-                const int c = nt * n_tile + chunk * 32 + unit * 4;
-                vb[i].v[0] = vb[i].v[1] = vb[i].v[2] = vb[i].v[3] = 0.f;
-                if (chunk < nchunk_b && dsrc[h]) {
-                    if (p.dy_vec && c + 3 < p.Cout) {
-                        const float4 q4 = __ldg(reinterpret_cast<const float4 *>(dsrc[h] + c));
-                        vb[i].v[0] = q4.x; vb[i].v[1] = q4.y; vb[i].v[2] = q4.z; vb[i].v[3] = q4.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < p.Cout) vb[i].v[e] = __ldg(dsrc[h] + c + e);
-                    }
-                }
-            }
-            mbar_wait(empty(s), ph ^ 1);
-            uint8_t *a_hi = sm + s * Smem::STAGE_BYTES, *a_lo = a_hi + A_BYTES;
-            uint8_t *b_hi = a_hi + 2 * A_BYTES, *b_lo = b_hi + MAX_N * 128;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int h = i & 1, chunk = i >> 1;
-                const int row = r0 + 16 * h;
-                const uint32_t off = (uint32_t)chunk * CHUNK_BYTES + mn_swizzle_off(row, unit);
-                const int cl = chunk * 32 + unit * 4;             // channel within the 128-channel tile
-                F4 hi, lo;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float a = va[i].v[e];
-                    if (has_aff) a = fmaf(a, s_scale[cl + e], s_shift[cl + e]);
-                    if (p.pre_relu) a = fmaxf(a, 0.f);
-                    if (!xsrc[h] || ci_tile * BLOCK_CI + cl + e >= p.Cin) a = 0.f;
-                    const float hh = rna_tf32(a);
-                    hi.v[e] = hh;
-                    lo.v[e] = rna_tf32(a - hh);
-                }
-                *reinterpret_cast<float4 *>(a_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
-                *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
-                if (chunk < nchunk_b) {
+                const int c = cbase + chunk * 32 + unit * 4;
+                const bool live = chunk < nchunk && ok[h] && c < cmax;
+                mk |= (live ? 1u : 0u) << i;
+                if (vec && (c + 3 < cmax || !live)) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(src + (live ? off[h] + c : 0)));
+                    v[i].v[0] = q4.x; v[i].v[1] = q4.y; v[i].v[2] = q4.z; v[i].v[3] = q4.w;
+                } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float a = vb[i].v[e];
-                        const float hh = rna_tf32(a);
-                        hi.v[e] = hh;
-                        lo.v[e] = rna_tf32(a - hh);
+                        const bool eok = live && (c + e < cmax);
+                        const float q1 = __ldg(src + (eok ? off[h] + c + e : 0));
+                        v[i].v[e] = eok ? q1 : 0.f;
                     }
-                    *reinterpret_cast<float4 *>(b_hi + off) = make_float4(hi.v[0], hi.v[1], hi.v[2], hi.v[3]);
-                    *reinterpret_cast<float4 *>(b_lo + off) = make_float4(lo.v[0], lo.v[1], lo.v[2], lo.v[3]);
+                }
+            }
+            mask = mk;
+        };
+        auto store_kb = [&](int it, F4(&v)[8], uint32_t mask) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(empty(s), ph ^ 1);
+            const uint32_t t_hi = base + s * Smem::STAGE_BYTES + tile_off;
+            const uint32_t t_lo = t_hi + lo_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int chunk = i >> 1;
+                if (chunk < nchunk) {
+                    const bool ok = (mask >> i) & 1u;
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = v[i].v[e];
+                        if (grp == 0) {
+                            if (has_aff) a = fmaf(a, sc[chunk][e], sh[chunk][e]);
+                            if (p.pre_relu) a = fmaxf(a, 0.f);
+                        }
+                        a = ok ? a : 0.f;
+                        const float hh = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+                        hi[e] = hh;
+                        lo[e] = a - hh;
+                    }
+                    st_shared_v4(t_hi + roff[i], hi[0], hi[1], hi[2], hi[3]);
+                    st_shared_v4(t_lo + roff[i], lo[0], lo[1], lo[2], lo[3]);
                 }
             }
             fence_proxy_async();
             mbar_arrive(full(s));
+        };
+        {
+            F4 va[8], vb[8];
+            uint32_t ma = 0, mb = 0;
+            int it = 0;
+            if (it < nkb) load_kb(it, va, ma);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load_kb(it + 1, vb, mb);
+                store_kb(it, va, ma);
+                if (more) {
+                    if (it + 2 < nkb) load_kb(it + 2, va, ma);
+                    store_kb(it + 1, vb, mb);
+                }
+            }
         }
 
         // ---- epilogue: TMEM lane = input channel, columns = output channels
@@ -315,6 +327,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     const long long M = (long long)B * p.Hout * p.Wout;
     if (p.Hout < 1 || p.Wout < 1 || M > 0x7ffffff0LL) return BTS_EINVAL;
+    if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL || M * dy_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;
     p.M = (int)M;
     p.n_tile = bts_conv_n_tile(Cout);
     p.part = workspace; p.splitK = splitK;
