@@ -80,6 +80,10 @@ SIGNATURES = {
     "bts_conv_wgrad_plan": [_i, _i, _i, _i, _i, _i, _i, _p, _p],
     "bts_conv_wgrad": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _i, _p, _i, _p, _ll, _ll,
                        _ll, _ll, _i, _p],
+    "bts_conv_c1_workspace_floats": [_i, _i],
+    "bts_conv_c1_fwd": [_p, _ll, _i, _i, _i, _i, _i, _p, _ll, _ll, _ll, _i, _p, _p],
+    "bts_conv_c1_dgrad": [_p, _p, _i, _i, _i, _i, _i, _p, _ll, _ll, _ll, _p, _ll, _p],
+    "bts_conv_c1_wgrad": [_p, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _ll, _p],
 }
 RESTYPES = {"bts_conv_packed_floats": ctypes.c_longlong}
 

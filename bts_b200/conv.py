@@ -17,6 +17,31 @@ ACT = {None: 0, "none": 0, "elu": 1, "sigmoid": 2}
 import os as _os
 WGRAD_BACKEND = _os.environ.get("BTS_B200_WGRAD", "tc")     # tc: tcgen05 wgrad kernel | aten: library scaffold
 
+TRACE = _os.environ.get("BTS_B200_TRACE", "0") == "1"     # per-call CUDA-event timing, aggregated by shape
+trace_log = []
+
+
+def _traced(kind, desc, fn):
+    if not TRACE:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    trace_log.append((kind, desc, e0, e1))
+    return out
+
+
+def trace_report():
+    torch.cuda.synchronize()
+    agg = {}
+    for kind, desc, e0, e1 in trace_log:
+        k = (kind, desc)
+        t, n = agg.get(k, (0.0, 0))
+        agg[k] = (t + e0.elapsed_time(e1), n + 1)
+    return sorted(((t, n, k) for k, (t, n) in agg.items()), reverse=True)
+
+
 _pack_cache = {}   # id(weight) -> (weakref, version, data_ptr, transpose) -> packed tensor
 
 
@@ -94,9 +119,11 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
         pre_scale = pre_scale.contiguous()
         pre_shift = pre_shift.contiguous()
     with torch.cuda.device(x.device):
-        rc = _lib.lib().bts_conv_fwd(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding, dilation,
-                                     _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift), int(pre_relu), _ptr(out), os_,
-                                     ACT[act], int(precision), _stream())
+        rc = _traced("dgrad" if transpose_flip else "fwd",
+                     "%dx%dx%d %d->%d k%d d%d s%d%s" % (B, Hs, Ws, Cin, Co, KH, dilation, stride, " up" if upsample2 else ""),
+                     lambda: _lib.lib().bts_conv_fwd(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
+                                                     dilation, _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift),
+                                                     int(pre_relu), _ptr(out), os_, ACT[act], int(precision), _stream()))
     _lib.check(rc, "bts_conv_fwd")
     _lib.count()
     return out
@@ -121,9 +148,12 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
     if pre_scale is not None:
         pre_scale, pre_shift = pre_scale.contiguous(), pre_shift.contiguous()
     with torch.cuda.device(x.device):
-        rc = L.bts_conv_wgrad(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding, dilation,
-                              _ptr(pre_scale), _ptr(pre_shift), int(pre_relu), _ptr(gy), gs, Cout, _ptr(ws), split.value,
-                              _ptr(gw), s[0], s[1], s[2], s[3], int(precision), _stream())
+        rc = _traced("wgrad", "%dx%dx%d %d->%d k%d d%d s%d%s" % (B, Hs, Ws, Cin, Cout, KH, dilation, stride,
+                                                                  " up" if upsample2 else ""),
+                     lambda: L.bts_conv_wgrad(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
+                                              dilation, _ptr(pre_scale), _ptr(pre_shift), int(pre_relu), _ptr(gy), gs,
+                                              Cout, _ptr(ws), split.value, _ptr(gw), s[0], s[1], s[2], s[3],
+                                              int(precision), _stream()))
     _lib.check(rc, "bts_conv_wgrad")
     _lib.count(2)
     return gw
@@ -164,3 +194,69 @@ class _ConvTC(torch.autograd.Function):
 
 def conv2d(x, weight, stride=1, padding=0, dilation=1):
     return _ConvTC.apply(x, weight, stride, padding, dilation)
+
+
+# ---------------------------------------------------------------------------- single-output-channel heads
+C1_CHANNELS = (8, 16, 32, 64, 128)
+
+
+def c1_eligible(weight, stride, padding, dilation):
+    co, ci, kh, kw = weight.shape
+    return (co == 1 and kh == kw and kh in (1, 3) and stride == 1 and dilation == 1 and padding == kh // 2
+            and ci in C1_CHANNELS)
+
+
+class _ConvC1(torch.autograd.Function):
+    """Cout = 1 convolution (+ optional fused sigmoid) on the HBM-bound CUDA-core kernels (csrc/thin.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, sigmoid):
+        _need_cuda(x, weight)
+        x, xs = _nhwc_view(x)
+        if xs % 4 != 0 or x.data_ptr() % 16 != 0:
+            x = x.contiguous(memory_format=torch.channels_last)
+            xs = x.shape[1]
+        B, C, H, W = x.shape
+        K = weight.shape[2]
+        y = torch.empty((B, 1, H, W), device=x.device, dtype=torch.float32)
+        s = weight.stride()
+        with torch.cuda.device(x.device):
+            rc = _traced("c1fwd", "%dx%dx%d %d->1 k%d" % (B, H, W, C, K),
+                         lambda: _lib.lib().bts_conv_c1_fwd(_ptr(x), xs, B, H, W, C, K, _ptr(weight), s[1], s[2], s[3],
+                                                            2 if sigmoid else 0, _ptr(y), _stream()))
+        _lib.check(rc, "bts_conv_c1_fwd")
+        _lib.count()
+        ctx.save_for_backward(x, weight, y if sigmoid else None)
+        ctx.xs = xs
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, sig = ctx.saved_tensors
+        B, C, H, W = x.shape
+        K = weight.shape[2]
+        gy = gy.contiguous()
+        s = weight.stride()
+        L = _lib.lib()
+        gx = gw = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+                rc = _traced("c1dgrad", "%dx%dx%d 1->%d k%d" % (B, H, W, C, K),
+                             lambda: L.bts_conv_c1_dgrad(_ptr(gy), _ptr(sig), B, H, W, C, K, _ptr(weight), s[1], s[2], s[3],
+                                                         _ptr(gx), C, _stream()))
+                _lib.check(rc, "bts_conv_c1_dgrad")
+                _lib.count()
+            if ctx.needs_input_grad[1]:
+                ws = torch.empty(L.bts_conv_c1_workspace_floats(C, K), device=x.device, dtype=torch.float32)
+                gw = torch.empty_strided(tuple(weight.shape), tuple(s), device=x.device, dtype=torch.float32)
+                rc = _traced("c1wgrad", "%dx%dx%d %d->1 k%d" % (B, H, W, C, K),
+                             lambda: L.bts_conv_c1_wgrad(_ptr(x), ctx.xs, _ptr(gy), _ptr(sig), B, H, W, C, K, _ptr(ws),
+                                                         _ptr(gw), s[1], s[2], s[3], _stream()))
+                _lib.check(rc, "bts_conv_c1_wgrad")
+                _lib.count(2)
+        return gx, gw, None
+
+
+def conv_c1(x, weight, sigmoid=False):
+    return _ConvC1.apply(x, weight, bool(sigmoid))

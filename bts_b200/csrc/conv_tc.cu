@@ -118,6 +118,9 @@ struct SmemLayout {
     static constexpr int TOTAL = BAR_OFF + 256;
 };
 
+// PRE: 0 none, 1 ReLU, 2 affine, 3 affine + ReLU (compile-time so the per-element producer code carries no dead ops)
+// UP : nearest x2 up-sample folded into the address map;  VEC: 16-byte aligned rows (float4 loads)
+template <int PRE, bool UP, bool VEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
@@ -212,11 +215,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int t = pt & 127;
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7
-        const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
+        const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
         const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
-        // per-row output pixel origin in input coordinates (fixed for the whole tile) and 32-bit element offsets
-        int oy[8], ox[8];
-        int rbase[8];                              // element offset of image b (row-valid) or -1 (row beyond M)
+        constexpr bool AFF = PRE >= 2;
+        constexpr bool RELU = (PRE & 1) != 0;
+        // per-row output-pixel origin in input coordinates (fixed for the tile).  Without up-sampling the source
+        // offset of tap (dy,dx) is rowoff + (dy*Ws+dx)*xs -- one add per row per k-block.
+        int oy[8], ox[8], rowoff[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
@@ -227,86 +232,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 const int b = q / p.Hout;
                 oy[i] = y * p.stride - p.pad;
                 ox[i] = x * p.stride - p.pad;
-                rbase[i] = b * p.Hs * p.Ws * xs;
+                rowoff[i] = b * p.Hs * p.Ws * xs + (UP ? 0 : (oy[i] * p.Ws + ox[i]) * xs);
             } else {
                 oy[i] = ox[i] = -0x40000000;       // never in bounds
-                rbase[i] = 0;
+                rowoff[i] = 0;
             }
         }
-        const bool has_aff = p.pre_scale != nullptr;
         const float *__restrict__ xg = p.x;
-        const uint32_t swz = (uint32_t)(chunk << 4);
         uint32_t roff[8];                          // swizzled byte offset of (row, chunk) inside a tile
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int row = r0 + 16 * i;
-            roff[i] = (uint32_t)row * 128u + (swz ^ (uint32_t)((row & 7) << 4));
+            roff[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         }
-        // ---- load phase: this lane's 8 x 16-byte global loads of one k-block, branch-free (out-of-image / out-of-
-        //      range lanes read element 0 -- always valid -- and are zeroed in the store phase)
-        auto load_kb = [&](int kb, F4(&v)[8], uint32_t &mask) {
-            const int tap = kb / p.KC, kc = kb - tap * p.KC;
-            const int ky = tap / p.KW;
-            const int dy = ky * p.dil, dx = (tap - ky * p.KW) * p.dil;
-            const int c = kc * 32 + chunk * 4;     // first channel of this lane's 16-byte unit
-            const bool cany = c < p.Cin;
-            const bool cfull = c + 3 < p.Cin;
+        // (tap, channel-chunk) of this group's current k-block, advanced incrementally (no divisions in the loop)
+        int l_tap = 0, l_kc = grp;                 // state of the LOAD stream
+        while (l_kc >= p.KC) { l_kc -= p.KC; ++l_tap; }
+        int l_ky = l_tap / p.KW, l_kx = l_tap - l_ky * p.KW;
+        auto advance_load = [&]() {
+            l_kc += 2;
+            while (l_kc >= p.KC) {
+                l_kc -= p.KC;
+                if (++l_kx == p.KW) { l_kx = 0; ++l_ky; }
+            }
+        };
+        // ---- load phase: this lane's 8 x 16-byte global loads of one k-block (predicated, branch-free)
+        auto load_kb = [&](F4(&v)[8], uint32_t &mask) {
+            const int dy = l_ky * p.dil, dx = l_kx * p.dil;
+            const int c = l_kc * 32 + chunk * 4;   // first channel of this lane's 16-byte unit
+            const int tapoff = UP ? 0 : (dy * p.Ws + dx) * xs + c;
             uint32_t mk = 0;
-            if (p.vec_ok && (cfull || !cany)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int yy = oy[i] + dy, xx = ox[i] + dx;
-                    const bool ok = cany && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
-                    const int off = ok ? rbase[i] + (sy * p.Ws + sx) * xs + c : 0;
-                    mk |= (ok ? 1u : 0u) << i;
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(xg + off));
+            for (int i = 0; i < 8; ++i) {
+                const int yy = oy[i] + dy, xx = ox[i] + dx;
+                const bool ok = (c < p.Cin) && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                mk |= (ok ? 1u : 0u) << i;
+                int off;
+                if (UP) off = rowoff[i] + ((yy >> 1) * p.Ws + (xx >> 1)) * xs + c;
+                else off = rowoff[i] + tapoff;
+                if (VEC) {
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) q = __ldg(reinterpret_cast<const float4 *>(xg + off));
                     v[i].v[0] = q.x; v[i].v[1] = q.y; v[i].v[2] = q.z; v[i].v[3] = q.w;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int yy = oy[i] + dy, xx = ox[i] + dx;
-                    const bool ok = cany && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
-                    const int off = ok ? rbase[i] + (sy * p.Ws + sx) * xs + c : 0;
-                    mk |= (ok ? 1u : 0u) << i;
+                } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const bool eok = ok && (c + e < p.Cin);
-                        const float q = __ldg(xg + (eok ? off + e : 0));
-                        v[i].v[e] = eok ? q : 0.f;
+                        float q = 0.f;
+                        if (ok && c + e < p.Cin) q = __ldg(xg + off + e);
+                        v[i].v[e] = q;
                     }
                 }
             }
             mask = mk;
+            advance_load();
         };
         // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
         //      hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is
         //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
+        int s_kc = grp % p.KC;                     // channel chunk of the STORE stream (for the affine params)
         auto store_kb = [&](int kb, F4(&v)[8], uint32_t mask) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
-            const int kc = kb % p.KC;
-            const int c = kc * 32 + chunk * 4;
             mbar_wait(empty(s), ph ^ 1);
             const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
-            float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-            if (has_aff) {
+            float sc[4], sh[4];
+            const int c = s_kc * 32 + chunk * 4;
+            s_kc += 2;
+            while (s_kc >= p.KC) s_kc -= p.KC;
+            if (AFF) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { sc[e] = s_scale[c + e]; sh[e] = s_shift[c + e]; }
             }
+            if (VEC && c < p.Cin && c + 3 >= p.Cin) {
+                // channel tail (Cin % 4 != 0, rows padded to 16 B): the float4 read past Cin -- zero those lanes
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int e = 1; e < 4; ++e)
+                        if (c + e >= p.Cin) v[i].v[e] = 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const bool ok = (mask >> i) & 1u;
                 float hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float a = v[i].v[e];
-                    if (has_aff) a = fmaf(a, sc[e], sh[e]);     // scale/shift are 0 beyond Cin
-                    if (p.pre_relu) a = fmaxf(a, 0.f);
-                    a = ok ? a : 0.f;                           // zero padding is applied after the pre-op
+                    if (AFF) {
+                        a = fmaf(a, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
+                        if (RELU) a = fmaxf(a, 0.f);
+                        a = ((mask >> i) & 1u) ? a : 0.f;       // zero padding is applied after the pre-op
+                    } else if (RELU) {
+                        a = fmaxf(a, 0.f);                      // padded lanes were loaded as 0
+                    }
                     const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
                     hi[e] = h;
                     lo[e] = a - h;
@@ -317,20 +335,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(full_a(s));
         };
-        // ---- software pipeline: the loads of this group's NEXT k-block are in flight while the current one is
-        //      transformed and stored (register ping-pong), so L2 latency hides behind a full k-block of work
+        // ---- software pipeline: the loads of this group's next TWO k-blocks are in flight while the current one is
+        //      transformed and stored (three rotating register buffers), so L2 latency stays hidden even when the
+        //      MMA time per k-block is short (small Cout)
         {
-            F4 va[8], vb[8];
-            uint32_t ma = 0, mb = 0;
+            F4 va[8], vb[8], vc[8];
+            uint32_t ma = 0, mb = 0, mc = 0;
+            const int total = (KB - grp + 1) >> 1;     // k-blocks of this group
+            int issued = 0;
             int kb = grp;
-            if (kb < KB) load_kb(kb, va, ma);
-            for (; kb < KB; kb += 4) {
-                const bool more = kb + 2 < KB;
-                if (more) load_kb(kb + 2, vb, mb);
+            if (issued < total) { load_kb(va, ma); ++issued; }
+            if (issued < total) { load_kb(vb, mb); ++issued; }
+            for (int done = 0; done < total; done += 3) {
+                if (issued < total) { load_kb(vc, mc); ++issued; }
                 store_kb(kb, va, ma);
-                if (more) {
-                    if (kb + 4 < KB) load_kb(kb + 4, va, ma);
-                    store_kb(kb + 2, vb, mb);
+                kb += 2;
+                if (done + 1 < total) {
+                    if (issued < total) { load_kb(va, ma); ++issued; }
+                    store_kb(kb, vb, mb);
+                    kb += 2;
+                }
+                if (done + 2 < total) {
+                    if (issued < total) { load_kb(vb, mb); ++issued; }
+                    store_kb(kb, vc, mc);
+                    kb += 2;
                 }
             }
         }
@@ -443,17 +471,36 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     p.KC = (Cin + 31) / 32;
     p.KB = KH * KW * p.KC;
     p.vec_ok = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SmemLayout::TOTAL + 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
     const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     if (m_tiles > 0x7fffffffLL) return BTS_EINVAL;
     dim3 grid((unsigned)m_tiles, (unsigned)p.n_tiles);
-    conv_tc_kernel<<<grid, NUM_THREADS, SmemLayout::TOTAL + 1024, (cudaStream_t)stream>>>(p);
+    const int pre = (pre_scale ? 2 : 0) | (p.pre_relu ? 1 : 0);
+    const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
+    cudaError_t err = cudaSuccess;
+#define BTS_LAUNCH(PRE, UP, VEC)                                                                                   \
+    do {                                                                                                           \
+        static bool attr_set = false;                                                                              \
+        if (!attr_set) {                                                                                           \
+            err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                       SmemLayout::TOTAL + 1024);                                                  \
+            if (err != cudaSuccess) return (int)err;                                                               \
+            attr_set = true;                                                                                       \
+        }                                                                                                          \
+        conv_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, SmemLayout::TOTAL + 1024, (cudaStream_t)stream>>>(p);    \
+    } while (0)
+#define BTS_DISPATCH_UV(PRE)                                  \
+    do {                                                      \
+        if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true); else BTS_LAUNCH(PRE, true, false); }   \
+        else { if (vec) BTS_LAUNCH(PRE, false, true); else BTS_LAUNCH(PRE, false, false); }      \
+    } while (0)
+    switch (pre) {
+        case 0: BTS_DISPATCH_UV(0); break;
+        case 1: BTS_DISPATCH_UV(1); break;
+        case 2: BTS_DISPATCH_UV(2); break;
+        default: BTS_DISPATCH_UV(3); break;
+    }
+#undef BTS_DISPATCH_UV
+#undef BTS_LAUNCH
     BTS_LAUNCH_CHECK();
     return 0;
 }

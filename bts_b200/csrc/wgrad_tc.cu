@@ -17,11 +17,12 @@ namespace {
 constexpr int BLOCK_CI = 128;
 constexpr int BLOCK_KP = 32;                 // pixels per k-block
 constexpr int MAX_N = 128;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;                    // split (hi/lo) operand stages the MMA reads
+constexpr int RAW_BYTES = 48 * 1024;         // per producer group: ring of raw fp32 tiles filled by cp.async
+constexpr int MAX_RING = 8;
 constexpr int CHUNK_BYTES = BLOCK_KP * 128;  // one 32-channel chunk of a k-block: 4 KB
 constexpr int A_BYTES = 4 * CHUNK_BYTES;     // 16 KB (hi or lo)
 constexpr int NUM_THREADS = 320;
-constexpr int MAX_CIN_SMEM = 4096;
 
 struct WgradParams {
     const float *x; long long xs;
@@ -39,17 +40,19 @@ struct WgradParams {
 
 struct Smem {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * MAX_N * 128;   // 64 KB
-    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = PRE_OFF + 2 * MAX_CIN_SMEM * 4;
+    static constexpr int RAW_OFF = STAGES * STAGE_BYTES;                 // 128 KB: then 2 x 48 KB raw rings
+    static constexpr int PRE_OFF = RAW_OFF + 2 * RAW_BYTES;
+    static constexpr int BAR_OFF = PRE_OFF + 2 * BLOCK_CI * 4;
     static constexpr int TOTAL = BAR_OFF + 256;
 };
 
+template <int PRE, bool UP, bool VEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
     float *s_scale = reinterpret_cast<float *>(sm + Smem::PRE_OFF);
-    float *s_shift = s_scale + MAX_CIN_SMEM;
+    float *s_shift = s_scale + BLOCK_CI;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + Smem::BAR_OFF);
     const uint32_t bar0 = base + Smem::BAR_OFF;
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -82,6 +85,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             s_shift[c] = ch < p.Cin ? p.pre_shift[ch] : 0.f;
         }
     }
+    // chunks of the A operand beyond the last live input channel are never produced: zero them once
+    for (int i = threadIdx.x; i < STAGES * 2 * A_BYTES / 16; i += NUM_THREADS) {
+        const int st_ = i / (2 * A_BYTES / 16), r_ = i % (2 * A_BYTES / 16);
+        st_shared_v4(base + st_ * Smem::STAGE_BYTES + r_ * 16, 0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -119,95 +128,130 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         const int t = pt & 127;
         const int unit = t & 7;                    // 16-byte unit of the 128-byte row
         const int r0 = t >> 3;                     // pixel rows r0, r0 + 16 of the 32-pixel k-block
-        const int Hin = p.up ? 2 * p.Hs : p.Hs, Win = p.up ? 2 * p.Ws : p.Ws;
-        const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
-        const bool has_aff = p.pre_scale != nullptr;
-        const int nchunk = grp == 0 ? 4 : ((n_tile + 31) >> 5);
-        const int cbase = grp == 0 ? ci_tile * BLOCK_CI : nt * n_tile;     // first channel of this tile
-        const int cmax = grp == 0 ? p.Cin : p.Cout;
-        const float *__restrict__ src = grp == 0 ? p.x : p.dy;
-        const bool vec = grp == 0 ? p.x_vec : p.dy_vec;
-        const int xs = (int)p.xs, dys = (int)p.dys;
-        const uint32_t tile_off = grp == 0 ? 0u : (uint32_t)(2 * A_BYTES);
-        const uint32_t lo_off = grp == 0 ? (uint32_t)A_BYTES : (uint32_t)(MAX_N * 128);
+        constexpr bool AFF = PRE >= 2;
+        constexpr bool RELU = (PRE & 1) != 0;
         uint32_t roff[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) roff[i] = (uint32_t)(i >> 1) * CHUNK_BYTES + mn_swizzle_off(r0 + 16 * (i & 1), unit);
-        float sc[4][4], sh[4][4];                  // per chunk, this lane's 4 channels (group 0 only)
+
+        // Every producer group streams its operand through a ring of RAW fp32 tiles filled by cp.async (LDGSTS, zero-fill
+        // for padding / tails): up to `ring` k-blocks of loads are in flight per thread without holding registers, which
+        // is what hides DRAM latency when the MMA time per k-block is short (small Cin/Cout).  Each thread later reads
+        // back exactly the 16-byte units it copied (no cross-thread hazard), applies the pre-op, splits hi/lo and writes
+        // the swizzled MN-major operand tiles of the split stage.
+        const int nlive = grp == 0 ? min(4, (p.Cin - ci_tile * BLOCK_CI + 31) >> 5) : ((n_tile + 31) >> 5);
+        const int raw_stage = nlive * CHUNK_BYTES;
+        const int ring = min(MAX_RING, RAW_BYTES / raw_stage);
+        const uint32_t raw_base = base + Smem::RAW_OFF + grp * RAW_BYTES;
+        const uint32_t tile_off = grp == 0 ? 0u : (uint32_t)(2 * A_BYTES);
+        const uint32_t lo_off = grp == 0 ? (uint32_t)A_BYTES : (uint32_t)(MAX_N * 128);
+        const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
+        const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
+        const int xs = (int)p.xs, dys = (int)p.dys;
+        const int cb = (grp == 0 ? ci_tile * BLOCK_CI : nt * n_tile) + unit * 4;
+        const int cmax = grp == 0 ? p.Cin : p.Cout;
+        const float *__restrict__ src = grp == 0 ? p.x : p.dy;
+        float sc[4][4], sh[4][4];
+        if (AFF && grp == 0) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
+            for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                sc[ch][e] = (has_aff && grp == 0) ? s_scale[ch * 32 + unit * 4 + e] : 1.f;
-                sh[ch][e] = (has_aff && grp == 0) ? s_shift[ch * 32 + unit * 4 + e] : 0.f;
-            }
-        auto load_kb = [&](int it, F4(&v)[8], uint32_t &mask) {
+                for (int e = 0; e < 4; ++e) {
+                    sc[ch][e] = s_scale[ch * 32 + unit * 4 + e];
+                    sh[ch][e] = s_shift[ch * 32 + unit * 4 + e];
+                }
+        }
+        // output-pixel coordinates of this thread's two rows, advanced by 32 pixels per k-block (no divisions)
+        int px[2], py[2], pb[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = kb0 * BLOCK_KP + r0 + 16 * h;
+            px[h] = m % p.Wout;
+            const int q = m / p.Wout;
+            py[h] = q % p.Hout;
+            pb[h] = q / p.Hout;
+        }
+        uint32_t maskring = 0;                     // 2 validity bits per in-flight k-block (x group, AFF only)
+        auto issue = [&](int it) {
             const int kb = kb0 + it;
+            const uint32_t rs = raw_base + (uint32_t)(it % ring) * (uint32_t)raw_stage;
             int off[2];
             bool ok[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int m = kb * BLOCK_KP + r0 + 16 * h;
                 ok[h] = m < p.M;
-                off[h] = 0;
                 if (grp == 0) {
-                    const int mm = ok[h] ? m : 0;
-                    const int x = mm % p.Wout;
-                    const int q = mm / p.Wout;
-                    const int y = q % p.Hout;
-                    const int b = q / p.Hout;
-                    const int yy = y * p.stride + dyo, xx = x * p.stride + dxo;
+                    const int yy = py[h] * p.stride + dyo, xx = px[h] * p.stride + dxo;
                     ok[h] = ok[h] && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                    const int sy = p.up ? (yy >> 1) : yy, sx = p.up ? (xx >> 1) : xx;
-                    if (ok[h]) off[h] = ((b * p.Hs + sy) * p.Ws + sx) * xs;
-                } else if (ok[h]) {
-                    off[h] = m * dys;
+                    const int sy = UP ? (yy >> 1) : yy, sx = UP ? (xx >> 1) : xx;
+                    off[h] = ok[h] ? ((pb[h] * p.Hs + sy) * p.Ws + sx) * xs + cb : 0;
+                    px[h] += BLOCK_KP;
+                    while (px[h] >= p.Wout) {
+                        px[h] -= p.Wout;
+                        if (++py[h] == p.Hout) { py[h] = 0; ++pb[h]; }
+                    }
+                } else {
+                    off[h] = ok[h] ? m * dys + cb : 0;
                 }
             }
-            uint32_t mk = 0;
+            maskring = (maskring << 2) | (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int h = i & 1, chunk = i >> 1;
-                const int c = cbase + chunk * 32 + unit * 4;
-                const bool live = chunk < nchunk && ok[h] && c < cmax;
-                mk |= (live ? 1u : 0u) << i;
-                if (vec && (c + 3 < cmax || !live)) {
-                    const float4 q4 = __ldg(reinterpret_cast<const float4 *>(src + (live ? off[h] + c : 0)));
-                    v[i].v[0] = q4.x; v[i].v[1] = q4.y; v[i].v[2] = q4.z; v[i].v[3] = q4.w;
-                } else {
+                if (chunk < nlive) {
+                    const int c = cb + chunk * 32;
+                    if (VEC) {
+                        const bool live = ok[h] && c < cmax;
+                        cp_async16(rs + roff[i], src + (live ? off[h] + chunk * 32 : 0), live ? 16u : 0u);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const bool eok = live && (c + e < cmax);
-                        const float q1 = __ldg(src + (eok ? off[h] + c + e : 0));
-                        v[i].v[e] = eok ? q1 : 0.f;
+                        for (int e = 0; e < 4; ++e) {
+                            const bool live = ok[h] && (c + e < cmax);
+                            cp_async4(rs + roff[i] + 4 * e, src + (live ? off[h] + chunk * 32 + e : 0), live ? 4u : 0u);
+                        }
                     }
                 }
             }
-            mask = mk;
         };
-        auto store_kb = [&](int it, F4(&v)[8], uint32_t mask) {
+        auto transform = [&](int it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
+            const uint32_t rs = raw_base + (uint32_t)(it % ring) * (uint32_t)raw_stage;
+            const uint32_t mk = (maskring >> (2 * (min(ring - 1, nkb - 1 - it)))) & 3u;   // bits pushed when `it` was issued
             mbar_wait(empty(s), ph ^ 1);
             const uint32_t t_hi = base + s * Smem::STAGE_BYTES + tile_off;
             const uint32_t t_lo = t_hi + lo_off;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int chunk = i >> 1;
-                if (chunk < nchunk) {
-                    const bool ok = (mask >> i) & 1u;
+                if (chunk < nlive) {
+                    const float4 q = ld_shared_v4(rs + roff[i]);
+                    float a[4] = {q.x, q.y, q.z, q.w};
+                    if (VEC) {           // channel tail of a 16-byte padded row: lanes past the last channel
+                        const int c = cb + chunk * 32;
+                        if (c + 3 >= cmax) {
+                            if (c + 1 >= cmax) a[1] = 0.f;
+                            if (c + 2 >= cmax) a[2] = 0.f;
+                            a[3] = 0.f;
+                        }
+                    }
                     float hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float a = v[i].v[e];
-                        if (grp == 0) {
-                            if (has_aff) a = fmaf(a, sc[chunk][e], sh[chunk][e]);
-                            if (p.pre_relu) a = fmaxf(a, 0.f);
+                        float v = a[e];
+                        if (PRE != 0 && grp == 0) {
+                            if (AFF) {
+                                v = fmaf(v, sc[chunk][e], sh[chunk][e]);
+                                if (RELU) v = fmaxf(v, 0.f);
+                                v = ((mk >> (i & 1)) & 1u) ? v : 0.f;   // zero padding applies after the pre-op
+                            } else {
+                                v = fmaxf(v, 0.f);
+                            }
                         }
-                        a = ok ? a : 0.f;
-                        const float hh = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+                        const float hh = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
                         hi[e] = hh;
-                        lo[e] = a - hh;
+                        lo[e] = v - hh;
                     }
                     st_shared_v4(t_hi + roff[i], hi[0], hi[1], hi[2], hi[3]);
                     st_shared_v4(t_lo + roff[i], lo[0], lo[1], lo[2], lo[3]);
@@ -216,21 +260,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             fence_proxy_async();
             mbar_arrive(full(s));
         };
-        {
-            F4 va[8], vb[8];
-            uint32_t ma = 0, mb = 0;
-            int it = 0;
-            if (it < nkb) load_kb(it, va, ma);
-            for (; it < nkb; it += 2) {
-                const bool more = it + 1 < nkb;
-                if (more) load_kb(it + 1, vb, mb);
-                store_kb(it, va, ma);
-                if (more) {
-                    if (it + 2 < nkb) load_kb(it + 2, va, ma);
-                    store_kb(it + 1, vb, mb);
-                }
-            }
+        for (int j = 0; j < ring - 1; ++j) {
+            if (j < nkb) issue(j);
+            cp_async_commit();
         }
+        for (int it = 0; it < nkb; ++it) {
+            const int j = it + ring - 1;
+            if (j < nkb) issue(j);
+            cp_async_commit();
+            cp_async_wait_dyn(ring - 1);
+            transform(it);
+        }
+        cp_async_wait_dyn(0);
 
         // ---- epilogue: TMEM lane = input channel, columns = output channels
         mbar_wait(accum_full, 0);
@@ -297,12 +338,20 @@ extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout,
     const int n_tile = bts_conv_n_tile(Cout);
     const long long tiles = (long long)((Cin + BLOCK_CI - 1) / BLOCK_CI) * ((Cout + n_tile - 1) / n_tile) * KH * KW;
     const int sms = bts_num_sms();
-    long long split = (2LL * sms + tiles - 1) / tiles;        // aim at ~2 waves of CTAs
-    if (split < 1) split = 1;
-    const long long max_split = (KBp + 15) / 16;              // at least 16 k-blocks (512 px) per CTA
-    if (split > max_split) split = max_split;
-    if (split < 1) split = 1;
-    if (split > 64) split = 64;
+    // split-K so that the CTA count fills whole waves of the SMs (a 297-CTA grid on 148 SMs wastes a third of the
+    // time in a 1-CTA tail): among splits giving <= 4 waves pick the best wave efficiency, ties -> more CTAs
+    long long max_split = (KBp + 15) / 16;                    // at least 16 k-blocks (512 px) per CTA
+    if (max_split < 1) max_split = 1;
+    if (max_split > 64) max_split = 64;
+    long long split = 1;
+    double best = -1.0;
+    for (long long sp = 1; sp <= max_split; ++sp) {
+        const long long ctas = tiles * sp;
+        const long long waves = (ctas + sms - 1) / sms;
+        if (waves > 4 && sp > 1) break;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff >= best - 1e-9) { best = eff; split = sp; }
+    }
     *splitK_out = (int)split;
     *workspace_floats = split * KH * KW * (long long)Cin * Cout;
     return 0;
@@ -336,17 +385,37 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     p.x_vec = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
     p.dy_vec = bts_aligned16(dy) && (dy_pixel_stride % 4 == 0);
     p.precision = precision;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL + 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
     const int taps = KH * KW;
     dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.n_tile - 1) / p.n_tile, taps * splitK);
     if (grid.z > 65535) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    wgrad_tc_kernel<<<grid, NUM_THREADS, Smem::TOTAL + 1024, st>>>(p);
+    const int pre = (pre_scale ? 2 : 0) | (p.pre_relu ? 1 : 0);
+    const bool vec = p.x_vec && p.dy_vec;   // aligned bases + pixel strides % 4 == 0 (channel tails masked in-kernel)
+    cudaError_t err = cudaSuccess;
+#define BTS_LAUNCH(PRE, UP, VEC)                                                                                    \
+    do {                                                                                                            \
+        static bool attr_set = false;                                                                               \
+        if (!attr_set) {                                                                                            \
+            err = cudaFuncSetAttribute(wgrad_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                       Smem::TOTAL + 1024);                                                         \
+            if (err != cudaSuccess) return (int)err;                                                                \
+            attr_set = true;                                                                                        \
+        }                                                                                                           \
+        wgrad_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, Smem::TOTAL + 1024, st>>>(p);                            \
+    } while (0)
+#define BTS_DISPATCH_UV(PRE)                                                                     \
+    do {                                                                                         \
+        if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true); else BTS_LAUNCH(PRE, true, false); }   \
+        else { if (vec) BTS_LAUNCH(PRE, false, true); else BTS_LAUNCH(PRE, false, false); }      \
+    } while (0)
+    switch (pre) {
+        case 0: BTS_DISPATCH_UV(0); break;
+        case 1: BTS_DISPATCH_UV(1); break;
+        case 2: BTS_DISPATCH_UV(2); break;
+        default: BTS_DISPATCH_UV(3); break;
+    }
+#undef BTS_DISPATCH_UV
+#undef BTS_LAUNCH
     BTS_LAUNCH_CHECK();
     const long long per = (long long)taps * Cin * Cout;
     long long g = (per + 255) / 256;

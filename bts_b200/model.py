@@ -61,8 +61,18 @@ class Conv2dTC(nn.Conv2d):
                 and self.dilation[0] == self.dilation[1] and self.kernel_size[0] == self.kernel_size[1]
                 and isinstance(self.padding, tuple) and self.padding_mode == "zeros"):
             from . import conv
+            if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
+                return conv.conv_c1(x, self.weight, sigmoid=False)
             return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0])
         return super().forward(x)
+
+    def forward_sigmoid(self, x):
+        """conv + Sigmoid in one kernel when this is a single-output-channel head (get_depth, reduc1x1.final)."""
+        if conv_backend() == "tc" and x.is_cuda and x.dtype == torch.float32:
+            from . import conv
+            if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
+                return conv.conv_c1(x, self.weight, sigmoid=True)
+        return torch.sigmoid(self.forward(x))
 
 
 def adopt_convs(module):
@@ -136,6 +146,10 @@ class reduction_1x1(nn.Sequential):
             cin, cout = cout, cout // 2
 
     def trunk(self, net):
+        if self.is_final:                       # last stage = Sequential(1x1 conv, Sigmoid): fused single-channel head
+            for name, m in self.reduc.named_children():
+                net = m[0].forward_sigmoid(net) if name == "final" else m(net)
+            return net
         return self.reduc(net)
 
     def forward(self, net):
@@ -161,6 +175,18 @@ class local_planar_guidance(nn.Module):
 
     def forward(self, plane_eq, focal=None):
         return ops.lpg(plane_eq, int(self.upratio))
+
+
+def _cat_pad4(tensors):
+    """torch.cat along channels whose result has 16-byte aligned NHWC rows: when the channel sum is not a multiple
+    of 4 (concat3: 225, concat2: 161) the slab gets zero channels appended and a view of the real ones is returned,
+    so the conv engine's 128-bit loads apply (the kernel masks the channel tail)."""
+    C = sum(t.shape[1] for t in tensors)
+    if C % 4 == 0 or not tensors[0].is_cuda:
+        return torch.cat(tensors, 1)
+    B, _, H, W = tensors[0].shape
+    pad = tensors[0].new_zeros((B, 4 - C % 4, H, W))
+    return torch.cat(list(tensors) + [pad], 1)[:, :C]
 
 
 class bts(nn.Module):
@@ -220,15 +246,15 @@ class bts(nn.Module):
 
         depth_8x8_scaled, d8_ds = ops.plane_head_lpg(self.reduc8x8.trunk(feat8), 8, md, ds_stride=4)
         x = self.bn3(self.upconv3(feat8))                                                 # H/4
-        iconv3 = self.conv3(torch.cat([x, skip1, d8_ds], 1))
+        iconv3 = self.conv3(_cat_pad4([x, skip1, d8_ds]))
         depth_4x4_scaled, d4_ds = ops.plane_head_lpg(self.reduc4x4.trunk(iconv3), 4, md, ds_stride=2)
         x = self.bn2(self.upconv2(iconv3))                                                # H/2
-        iconv2 = self.conv2(torch.cat([x, skip0, d4_ds], 1))
+        iconv2 = self.conv2(_cat_pad4([x, skip0, d4_ds]))
         depth_2x2_scaled = ops.plane_head_lpg(self.reduc2x2.trunk(iconv2), 2, md)
         up1 = self.upconv1(iconv2)                                                        # H
         reduc1x1 = self.reduc1x1(up1)
         iconv1 = self.conv1(torch.cat([up1, reduc1x1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled], 1))
-        final_depth = md * self.get_depth(iconv1)
+        final_depth = md * self.get_depth[0].forward_sigmoid(iconv1)      # Sequential(3x3 conv 32->1, Sigmoid), fused
         if self.params.dataset == "kitti":
             final_depth = final_depth * focal.view(-1, 1, 1, 1).float() / 715.0873
         return depth_8x8_scaled, depth_4x4_scaled, depth_2x2_scaled, reduc1x1, final_depth

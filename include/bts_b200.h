@@ -120,6 +120,21 @@ int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, int Hs, int 
                    float *dw, long long s_co, long long s_ci, long long s_kh, long long s_kw, int precision,
                    void *stream);
 
+/* ---- single-output-channel convolutions (get_depth 3x3 32->1 + sigmoid, bts.py:193-194; reduc1x1 final 1x1 8->1 +
+ * sigmoid, bts.py:94-96) as HBM-bound CUDA-core kernels.  x NHWC, C in {8,16,32,64,128}, K in {1,3}, stride 1,
+ * pad K/2.  w: the (1,C,K,K) parameter addressed by its (ci,kh,kw) strides.  act: 0 none, 2 sigmoid.
+ * Backward entry points take dy and, when the forward applied the sigmoid, the saved output `sig` (else NULL):
+ * the effective gradient is dy*sig*(1-sig).  wgrad needs bts_conv_c1_workspace_floats(C,K) floats of workspace. */
+int bts_conv_c1_workspace_floats(int C, int K);
+int bts_conv_c1_fwd(const float *x, long long x_pixel_stride, int B, int H, int W, int C, int K, const float *w,
+                    long long s_ci, long long s_kh, long long s_kw, int act, float *y, void *stream);
+int bts_conv_c1_dgrad(const float *dy, const float *sig, int B, int H, int W, int C, int K, const float *w,
+                      long long s_ci, long long s_kh, long long s_kw, float *dx, long long dx_pixel_stride,
+                      void *stream);
+int bts_conv_c1_wgrad(const float *x, long long x_pixel_stride, const float *dy, const float *sig, int B, int H,
+                      int W, int C, int K, float *workspace, float *dw, long long s_ci, long long s_kh,
+                      long long s_kw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

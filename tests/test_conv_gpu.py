@@ -113,3 +113,26 @@ def test_conv_autograd_dgrad_on_engine(k, pad, dil):
     conv.conv2d(xc, wc, 1, pad, dil).backward(gy.cuda())
     assert (xc.grad.cpu().double() - xd.grad).abs().max() / xd.grad.abs().max() < 2e-5
     assert (wc.grad.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("C,K,sig", [(32, 3, True), (8, 1, True), (32, 3, False), (64, 3, False), (16, 1, False)])
+def test_single_output_channel_head_kernels(C, K, sig):
+    """get_depth (3x3 32->1 + sigmoid) / reduc1x1.final (1x1 8->1 + sigmoid): CUDA-core streaming kernels, fp32 FMA --
+    fwd, dgrad and wgrad vs torch fp64."""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(C + K)
+    x = torch.randn(2, C, 13, 17, generator=g)
+    w = torch.randn(1, C, K, K, generator=g) / (C * K * K) ** 0.5
+    gy = torch.randn(2, 1, 13, 17, generator=g)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yd = F.conv2d(xd, wd, None, 1, K // 2)
+    if sig:
+        yd = torch.sigmoid(yd)
+    yd.backward(gy.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wc = w.cuda().requires_grad_(True)
+    y = conv.conv_c1(xc, wc, sigmoid=sig)
+    y.backward(gy.cuda())
+    assert (y.detach().cpu().double() - yd.detach()).abs().max() < 1e-5
+    assert (xc.grad.cpu().double() - xd.grad).abs().max() / xd.grad.abs().max() < 1e-5
+    assert (wc.grad.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max() < 1e-5
