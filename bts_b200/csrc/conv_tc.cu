@@ -17,14 +17,19 @@
 // ~2^-21 per product: fp32-grade).  Single-pass TF32 is available as an explicitly
 // labelled fast mode (precision=1) and is NOT used for parity.
 //
-// Warp roles (320 threads, 1 CTA/SM):
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... with the smem stage
+// ring, the two TMEM accumulators and all warp roles running continuously across tile boundaries (the MMA of tile
+// t+1 overlaps the epilogue of tile t; no per-tile launch / TMEM-alloc / pipeline-fill cost -- measured ~10 k cycles
+// per tile in the one-tile-per-CTA version, which dominated every small-K layer).
+// Warp roles (448 threads, 1 CTA/SM):
 //   warp 0      : weight loader -- one elected thread streams pre-packed, pre-split, pre-swizzled weight tiles
 //                 with 1-D bulk async copies (cp.async.bulk -> UBLKCP) completing on an mbarrier;
 //   warp 1      : TMEM allocator + MMA issuer -- one elected thread issues tcgen05.mma, commits to mbarriers;
 //   warps 2..9  : two producer groups (alternating k-blocks): coalesced 128-bit global loads of the activation
 //                 tile (8 lanes cover one pixel's 128 B), pre-op + hi/lo split in registers, swizzled 128-bit
-//                 shared stores of both halves, fence.proxy.async, mbarrier arrive; afterwards the same warps
-//                 run the epilogue: tcgen05.ld of the accumulator rows, activation, vectorised NHWC stores.
+//                 shared stores of both halves, fence.proxy.async, mbarrier arrive;
+//   warps 10..13: epilogue: wait for the tile's accumulator, tcgen05.ld of the 128 rows, activation, vectorised
+//                 NHWC stores, then hand the TMEM accumulator back to the MMA warp.
 #include "tc_common.cuh"
 
 namespace {
@@ -34,9 +39,11 @@ constexpr int BLOCK_K = 32;                 // fp32 elements per k-block = one 1
 constexpr int MAX_N = 128;
 constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB (hi or lo)
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 448;
 constexpr int PRODUCER_THREADS = 128;       // per group
 constexpr int MAX_CIN_SMEM = 4096;          // pre-op scale/shift staged in smem
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 256;              // two 128-column fp32 accumulators
 
 struct ConvParams {
     const float *x;          // NHWC source, pixel stride xs floats
@@ -57,6 +64,7 @@ struct ConvParams {
     int precision;           // 0: 3xTF32 (parity), 1: 1xTF32 (fast, labelled)
     int vec_ok;              // 16-byte aligned rows -> float4 loads
     long long M;             // B*Hout*Wout
+    int m_tiles, total_tiles;
     int KC;                  // ceil(Cin/32)
     int KB;                  // KH*KW*KC k-blocks
 };
@@ -129,18 +137,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     float *s_scale = reinterpret_cast<float *>(sm + SmemLayout::PRE_OFF);
     float *s_shift = s_scale + MAX_CIN_SMEM;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SmemLayout::BAR_OFF);
-    // bars: [0..S) full_a, [S..2S) full_b, [2S..3S) empty, [3S] accum_full; then the TMEM base address word
+    // bars: [0..S) full_a, [S..2S) full_b, [2S..3S) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base word
     const uint32_t bar0 = base + SmemLayout::BAR_OFF;
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    const uint32_t accum_full = bar0 + 8u * (3 * STAGES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 1);
+    auto tmem_full = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
+    auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, nt = blockIdx.y;
     const int n_tile = p.n_tile;
     const int KB = p.KB;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...   (tile -> m_tile = tile / n_tiles, nt = tile % n_tiles)
+    const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_kb = my_tiles * KB;          // host guarantees < 2^31
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -148,11 +159,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
-        mbar_init(accum_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), EPI_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
-    if (p.pre_scale) {
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (PRE >= 2) {
         for (int c = threadIdx.x; c < p.KC * 32; c += NUM_THREADS) {
             s_scale[c] = c < p.Cin ? p.pre_scale[c] : 0.f;
             s_shift[c] = c < p.Cin ? p.pre_shift[c] : 0.f;
@@ -167,51 +181,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ===================== weight loader =====================
         if (lane == 0) {
             const uint32_t bytes = 2u * (uint32_t)n_tile * 128u;
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * bytes;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty(s), ph ^ 1);
-                mbar_arrive_expect_tx(full_b(s), bytes);
-                bulk_copy_g2s(base + s * SmemLayout::STAGE_BYTES + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
+            int gk = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int nt = tile % p.n_tiles;
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * bytes;
+                for (int kb = 0; kb < KB; ++kb, ++gk) {
+                    const int s = gk % STAGES;
+                    const uint32_t ph = (uint32_t)(gk / STAGES) & 1;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full_b(s), bytes);
+                    bulk_copy_g2s(base + s * SmemLayout::STAGE_BYTES + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+            int gk = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int acc = ti & 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
-                const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                const uint32_t b_lo = b_hi + n_tile * 128;
-                const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-                if (p.precision == 0) {
+                for (int kb = 0; kb < KB; ++kb, ++gk) {
+                    const int s = gk % STAGES;
+                    const uint32_t ph = (uint32_t)(gk / STAGES) & 1;
+                    mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                    const uint32_t b_lo = b_hi + n_tile * 128;
+                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+                    if (p.precision == 0) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
-                        umma_tf32(tmem_base, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
+                            umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(tmem_base, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, 1);
-                } else {
+                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 8; ++k)
-                        umma_tf32(tmem_base, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BLOCK_K / 8; ++k)
+                            umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty(s));       // frees the stage when these MMAs have read it
                 }
-                umma_commit(empty(s));       // frees the stage when these MMAs have read it
+                umma_commit(tmem_full(acc));     // accumulator of this tile complete
             }
-            umma_commit(accum_full);
         }
-    } else {
+    } else if (warp < 10) {
         // ===================== activation producers (2 groups x 4 warps) =====================
         const int pt = threadIdx.x - 64;           // 0..255
-        const int grp = pt >> 7;                   // producer group: k-blocks kb == grp (mod 2)
+        const int grp = pt >> 7;                   // producer group: global k-blocks gk == grp (mod 2)
         const int t = pt & 127;
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7
@@ -219,25 +245,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
         constexpr bool AFF = PRE >= 2;
         constexpr bool RELU = (PRE & 1) != 0;
-        // per-row output-pixel origin in input coordinates (fixed for the tile).  Without up-sampling the source
-        // offset of tap (dy,dx) is rowoff + (dy*Ws+dx)*xs -- one add per row per k-block.
-        int oy[8], ox[8], rowoff[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
-            if (m < p.M) {
-                const int x = (int)(m % p.Wout);
-                const int q = (int)(m / p.Wout);
-                const int y = q % p.Hout;
-                const int b = q / p.Hout;
-                oy[i] = y * p.stride - p.pad;
-                ox[i] = x * p.stride - p.pad;
-                rowoff[i] = b * p.Hs * p.Ws * xs + (UP ? 0 : (oy[i] * p.Ws + ox[i]) * xs);
-            } else {
-                oy[i] = ox[i] = -0x40000000;       // never in bounds
-                rowoff[i] = 0;
-            }
-        }
         const float *__restrict__ xg = p.x;
         uint32_t roff[8];                          // swizzled byte offset of (row, chunk) inside a tile
 #pragma unroll
@@ -245,21 +252,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             const int row = r0 + 16 * i;
             roff[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         }
-        // (tap, channel-chunk) of this group's current k-block, advanced incrementally (no divisions in the loop)
-        int l_tap = 0, l_kc = grp;                 // state of the LOAD stream
-        while (l_kc >= p.KC) { l_kc -= p.KC; ++l_tap; }
-        int l_ky = l_tap / p.KW, l_kx = l_tap - l_ky * p.KW;
-        auto advance_load = [&]() {
-            l_kc += 2;
-            while (l_kc >= p.KC) {
-                l_kc -= p.KC;
-                if (++l_kx == p.KW) { l_kx = 0; ++l_ky; }
+        // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block to load, with the per-row output
+        //      pixel origin of that tile in input coordinates
+        int oy[8], ox[8], rowoff[8];
+        int l_ti = -1;
+        int l_gk = grp;
+        auto set_tile = [&](int ti) {
+            l_ti = ti;
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m_tile = tile / p.n_tiles;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
+                if (m < p.M) {
+                    const int x = (int)(m % p.Wout);
+                    const int q = (int)(m / p.Wout);
+                    const int y = q % p.Hout;
+                    const int b = q / p.Hout;
+                    oy[i] = y * p.stride - p.pad;
+                    ox[i] = x * p.stride - p.pad;
+                    rowoff[i] = b * p.Hs * p.Ws * xs + (UP ? 0 : (oy[i] * p.Ws + ox[i]) * xs);
+                } else {
+                    oy[i] = ox[i] = -0x40000000;   // never in bounds
+                    rowoff[i] = 0;
+                }
             }
         };
         // ---- load phase: this lane's 8 x 16-byte global loads of one k-block (predicated, branch-free)
         auto load_kb = [&](F4(&v)[8], uint32_t &mask) {
-            const int dy = l_ky * p.dil, dx = l_kx * p.dil;
-            const int c = l_kc * 32 + chunk * 4;   // first channel of this lane's 16-byte unit
+            const int ti = l_gk / KB;
+            const int kb = l_gk - ti * KB;
+            if (ti != l_ti) set_tile(ti);
+            const int tap = kb / p.KC, kc = kb - tap * p.KC;
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            const int dy = ky * p.dil, dx = kx * p.dil;
+            const int c = kc * 32 + chunk * 4;     // first channel of this lane's 16-byte unit
             const int tapoff = UP ? 0 : (dy * p.Ws + dx) * xs + c;
             uint32_t mk = 0;
 #pragma unroll
@@ -284,22 +311,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 }
             }
             mask = mk;
-            advance_load();
+            l_gk += 2;
         };
         // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
         //      hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is
         //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
-        int s_kc = grp % p.KC;                     // channel chunk of the STORE stream (for the affine params)
-        auto store_kb = [&](int kb, F4(&v)[8], uint32_t mask) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
+        int s_gk = grp;
+        auto store_kb = [&](F4(&v)[8], uint32_t mask) {
+            const int s = s_gk % STAGES;
+            const uint32_t ph = (uint32_t)(s_gk / STAGES) & 1;
+            const int kb = s_gk % KB;
+            const int c = (kb % p.KC) * 32 + chunk * 4;
+            s_gk += 2;
             mbar_wait(empty(s), ph ^ 1);
             const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
             float sc[4], sh[4];
-            const int c = s_kc * 32 + chunk * 4;
-            s_kc += 2;
-            while (s_kc >= p.KC) s_kc -= p.KC;
             if (AFF) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { sc[e] = s_scale[c + e]; sh[e] = s_shift[c + e]; }
@@ -335,74 +362,71 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(full_a(s));
         };
-        // ---- software pipeline: the loads of this group's next TWO k-blocks are in flight while the current one is
-        //      transformed and stored (three rotating register buffers), so L2 latency stays hidden even when the
-        //      MMA time per k-block is short (small Cout)
+        // ---- software pipeline (register ping-pong): the loads of this group's next k-block -- possibly of the next
+        //      tile -- are in flight while the current one is transformed and stored
         {
-            F4 va[8], vb[8], vc[8];
-            uint32_t ma = 0, mb = 0, mc = 0;
-            const int total = (KB - grp + 1) >> 1;     // k-blocks of this group
+            F4 va[8], vb[8];
+            uint32_t ma = 0, mb = 0;
+            const int mine = (total_kb - grp + 1) >> 1;   // k-blocks of this group
             int issued = 0;
-            int kb = grp;
-            if (issued < total) { load_kb(va, ma); ++issued; }
-            if (issued < total) { load_kb(vb, mb); ++issued; }
-            for (int done = 0; done < total; done += 3) {
-                if (issued < total) { load_kb(vc, mc); ++issued; }
-                store_kb(kb, va, ma);
-                kb += 2;
-                if (done + 1 < total) {
-                    if (issued < total) { load_kb(va, ma); ++issued; }
-                    store_kb(kb, vb, mb);
-                    kb += 2;
-                }
-                if (done + 2 < total) {
-                    if (issued < total) { load_kb(vb, mb); ++issued; }
-                    store_kb(kb, vc, mc);
-                    kb += 2;
+            if (issued < mine) { load_kb(va, ma); ++issued; }
+            for (int done = 0; done < mine; done += 2) {
+                if (issued < mine) { load_kb(vb, mb); ++issued; }
+                store_kb(va, ma);
+                if (done + 1 < mine) {
+                    if (issued < mine) { load_kb(va, ma); ++issued; }
+                    store_kb(vb, mb);
                 }
             }
         }
-
-        // ===================== epilogue (same 8 warps) =====================
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
+    } else {
+        // ===================== epilogue warps (10..13) =====================
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        const long long m = (long long)m_tile * BLOCK_M + row;
-        const int half = n_tile >> 1;                            // columns per producer group
-        const int col0 = grp * half;
-        float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
-        const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0) && ((n_tile & 3) == 0);
-        for (int cc = 0; cc < half; cc += 8) {
-            uint32_t r[8];
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cc), r);
-            tmem_ld_wait();
-            float o[8];
+        const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m_tile = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int acc = ti & 1;
+            const long long m = (long long)m_tile * BLOCK_M + row;
+            float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
+            mbar_wait(tmem_full(acc), (uint32_t)((ti >> 1) & 1));
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+            for (int cc = 0; cc < n_tile; cc += 16) {
+                uint32_t r[16];
+                tmem_ld8(t_addr + (uint32_t)cc, reinterpret_cast<uint32_t(&)[8]>(r[0]));
+                tmem_ld8(t_addr + (uint32_t)cc + 8, reinterpret_cast<uint32_t(&)[8]>(r[8]));
+                tmem_ld_wait();
+                if (m < p.M) {
+                    const int cbase = nt * n_tile + cc;          // absolute output channel
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float a = __uint_as_float(r[e]);
-                if (p.act == 1) a = a > 0.f ? a : expm1f(a);
-                else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
-                o[e] = a;
-            }
-            if (m < p.M) {
-                const int cbase = nt * n_tile + col0 + cc;       // absolute output channel
+                    for (int e4 = 0; e4 < 16; e4 += 4) {
+                        float o[4];
 #pragma unroll
-                for (int e4 = 0; e4 < 8; e4 += 4) {
-                    if (ovec && cbase + e4 + 3 < p.Cout) {
-                        *reinterpret_cast<float4 *>(orow + col0 + cc + e4) = make_float4(o[e4], o[e4 + 1], o[e4 + 2], o[e4 + 3]);
-                    } else {
+                        for (int e = 0; e < 4; ++e) {
+                            float a = __uint_as_float(r[e4 + e]);
+                            if (p.act == 1) a = a > 0.f ? a : expm1f(a);
+                            else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
+                            o[e] = a;
+                        }
+                        if (ovec && cbase + e4 + 3 < p.Cout) {
+                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (cbase + e4 + e < p.Cout) orow[col0 + cc + e4 + e] = o[e4 + e];
+                            for (int e = 0; e < 4; ++e)
+                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = o[e];
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(tmem_empty(acc));        // this thread is done reading the accumulator
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 128);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
@@ -472,8 +496,11 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     p.KB = KH * KW * p.KC;
     p.vec_ok = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
     const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    if (m_tiles > 0x7fffffffLL) return BTS_EINVAL;
-    dim3 grid((unsigned)m_tiles, (unsigned)p.n_tiles);
+    if (m_tiles * p.n_tiles * (long long)p.KB > 0x7fffffffLL) return BTS_EINVAL;
+    p.m_tiles = (int)m_tiles;
+    p.total_tiles = (int)(m_tiles * p.n_tiles);
+    const int sms = bts_num_sms();
+    dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     const int pre = (pre_scale ? 2 : 0) | (p.pre_relu ? 1 : 0);
     const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
     cudaError_t err = cudaSuccess;

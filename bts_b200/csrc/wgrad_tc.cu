@@ -17,9 +17,7 @@ namespace {
 constexpr int BLOCK_CI = 128;
 constexpr int BLOCK_KP = 32;                 // pixels per k-block
 constexpr int MAX_N = 128;
-constexpr int STAGES = 2;                    // split (hi/lo) operand stages the MMA reads
-constexpr int RAW_BYTES = 48 * 1024;         // per producer group: ring of raw fp32 tiles filled by cp.async
-constexpr int MAX_RING = 8;
+constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = BLOCK_KP * 128;  // one 32-channel chunk of a k-block: 4 KB
 constexpr int A_BYTES = 4 * CHUNK_BYTES;     // 16 KB (hi or lo)
 constexpr int NUM_THREADS = 320;
@@ -40,8 +38,7 @@ struct WgradParams {
 
 struct Smem {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * MAX_N * 128;   // 64 KB
-    static constexpr int RAW_OFF = STAGES * STAGE_BYTES;                 // 128 KB: then 2 x 48 KB raw rings
-    static constexpr int PRE_OFF = RAW_OFF + 2 * RAW_BYTES;
+    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = PRE_OFF + 2 * BLOCK_CI * 4;
     static constexpr int TOTAL = BAR_OFF + 256;
 };
@@ -134,144 +131,190 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
 #pragma unroll
         for (int i = 0; i < 8; ++i) roff[i] = (uint32_t)(i >> 1) * CHUNK_BYTES + mn_swizzle_off(r0 + 16 * (i & 1), unit);
 
-        // Every producer group streams its operand through a ring of RAW fp32 tiles filled by cp.async (LDGSTS, zero-fill
-        // for padding / tails): up to `ring` k-blocks of loads are in flight per thread without holding registers, which
-        // is what hides DRAM latency when the MMA time per k-block is short (small Cin/Cout).  Each thread later reads
-        // back exactly the 16-byte units it copied (no cross-thread hazard), applies the pre-op, splits hi/lo and writes
-        // the swizzled MN-major operand tiles of the split stage.
-        const int nlive = grp == 0 ? min(4, (p.Cin - ci_tile * BLOCK_CI + 31) >> 5) : ((n_tile + 31) >> 5);
-        const int raw_stage = nlive * CHUNK_BYTES;
-        const int ring = min(MAX_RING, RAW_BYTES / raw_stage);
-        const uint32_t raw_base = base + Smem::RAW_OFF + grp * RAW_BYTES;
-        const uint32_t tile_off = grp == 0 ? 0u : (uint32_t)(2 * A_BYTES);
-        const uint32_t lo_off = grp == 0 ? (uint32_t)A_BYTES : (uint32_t)(MAX_N * 128);
-        const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
-        const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
-        const int xs = (int)p.xs, dys = (int)p.dys;
-        const int cb = (grp == 0 ? ci_tile * BLOCK_CI : nt * n_tile) + unit * 4;
-        const int cmax = grp == 0 ? p.Cin : p.Cout;
-        const float *__restrict__ src = grp == 0 ? p.x : p.dy;
-        float sc[4][4], sh[4][4];
-        if (AFF && grp == 0) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    sc[ch][e] = s_scale[ch * 32 + unit * 4 + e];
-                    sh[ch][e] = s_shift[ch * 32 + unit * 4 + e];
-                }
-        }
-        // output-pixel coordinates of this thread's two rows, advanced by 32 pixels per k-block (no divisions)
-        int px[2], py[2], pb[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int m = kb0 * BLOCK_KP + r0 + 16 * h;
-            px[h] = m % p.Wout;
-            const int q = m / p.Wout;
-            py[h] = q % p.Hout;
-            pb[h] = q / p.Hout;
-        }
-        uint32_t maskring = 0;                     // 2 validity bits per in-flight k-block (x group, AFF only)
-        auto issue = [&](int it) {
-            const int kb = kb0 + it;
-            const uint32_t rs = raw_base + (uint32_t)(it % ring) * (uint32_t)raw_stage;
-            int off[2];
-            bool ok[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = kb * BLOCK_KP + r0 + 16 * h;
-                ok[h] = m < p.M;
-                if (grp == 0) {
-                    const int yy = py[h] * p.stride + dyo, xx = px[h] * p.stride + dxo;
-                    ok[h] = ok[h] && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                    const int sy = UP ? (yy >> 1) : yy, sx = UP ? (xx >> 1) : xx;
-                    off[h] = ok[h] ? ((pb[h] * p.Hs + sy) * p.Ws + sx) * xs + cb : 0;
-                    px[h] += BLOCK_KP;
-                    while (px[h] >= p.Wout) {
-                        px[h] -= p.Wout;
-                        if (++py[h] == p.Hout) { py[h] = 0; ++pb[h]; }
-                    }
-                } else {
-                    off[h] = ok[h] ? m * dys + cb : 0;
-                }
-            }
-            maskring = (maskring << 2) | (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+        // hi/lo split + swizzled stores of up to 8 units (4 chunks x 2 rows); only `nlive` chunks are written
+        // (the A regions were zeroed once, so dead channel chunks stay zero)
+        auto split_store = [&](uint32_t t_hi, uint32_t t_lo, F4(&v)[8], int nlive) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int h = i & 1, chunk = i >> 1;
-                if (chunk < nlive) {
-                    const int c = cb + chunk * 32;
-                    if (VEC) {
-                        const bool live = ok[h] && c < cmax;
-                        cp_async16(rs + roff[i], src + (live ? off[h] + chunk * 32 : 0), live ? 16u : 0u);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const bool live = ok[h] && (c + e < cmax);
-                            cp_async4(rs + roff[i] + 4 * e, src + (live ? off[h] + chunk * 32 + e : 0), live ? 4u : 0u);
-                        }
-                    }
-                }
-            }
-        };
-        auto transform = [&](int it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            const uint32_t rs = raw_base + (uint32_t)(it % ring) * (uint32_t)raw_stage;
-            const uint32_t mk = (maskring >> (2 * (min(ring - 1, nkb - 1 - it)))) & 3u;   // bits pushed when `it` was issued
-            mbar_wait(empty(s), ph ^ 1);
-            const uint32_t t_hi = base + s * Smem::STAGE_BYTES + tile_off;
-            const uint32_t t_lo = t_hi + lo_off;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int chunk = i >> 1;
-                if (chunk < nlive) {
-                    const float4 q = ld_shared_v4(rs + roff[i]);
-                    float a[4] = {q.x, q.y, q.z, q.w};
-                    if (VEC) {           // channel tail of a 16-byte padded row: lanes past the last channel
-                        const int c = cb + chunk * 32;
-                        if (c + 3 >= cmax) {
-                            if (c + 1 >= cmax) a[1] = 0.f;
-                            if (c + 2 >= cmax) a[2] = 0.f;
-                            a[3] = 0.f;
-                        }
-                    }
+                if ((i >> 1) < nlive) {
                     float hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float v = a[e];
-                        if (PRE != 0 && grp == 0) {
-                            if (AFF) {
-                                v = fmaf(v, sc[chunk][e], sh[chunk][e]);
-                                if (RELU) v = fmaxf(v, 0.f);
-                                v = ((mk >> (i & 1)) & 1u) ? v : 0.f;   // zero padding applies after the pre-op
-                            } else {
-                                v = fmaxf(v, 0.f);
-                            }
-                        }
-                        const float hh = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+                        const float a = v[i].v[e];
+                        const float hh = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
                         hi[e] = hh;
-                        lo[e] = v - hh;
+                        lo[e] = a - hh;
                     }
                     st_shared_v4(t_hi + roff[i], hi[0], hi[1], hi[2], hi[3]);
                     st_shared_v4(t_lo + roff[i], lo[0], lo[1], lo[2], lo[3]);
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(full(s));
         };
-        for (int j = 0; j < ring - 1; ++j) {
-            if (j < nkb) issue(j);
-            cp_async_commit();
+
+        if (grp == 0) {
+            // ------------------------------ x tiles (A operand): 4 chunks of 32 input channels ------------------
+            const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
+            const int dyo = (tap / p.KW) * p.dil - p.pad, dxo = (tap % p.KW) * p.dil - p.pad;
+            const int xs = (int)p.xs;
+            const int cb = ci_tile * BLOCK_CI + unit * 4;
+            int nlive = (p.Cin - ci_tile * BLOCK_CI + 31) >> 5;      // chunks that hold real channels
+            if (nlive > 4) nlive = 4;
+            float sc[4][4], sh[4][4];
+            if (AFF) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        sc[ch][e] = s_scale[ch * 32 + unit * 4 + e];
+                        sh[ch][e] = s_shift[ch * 32 + unit * 4 + e];
+                    }
+            }
+            const float *__restrict__ xg = p.x;
+            // output-pixel coordinates of this thread's two rows, advanced by 32 pixels per k-block (no divisions)
+            int px[2], py[2], pb[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = kb0 * BLOCK_KP + r0 + 16 * h;
+                px[h] = m % p.Wout;
+                const int q = m / p.Wout;
+                py[h] = q % p.Hout;
+                pb[h] = q / p.Hout;
+            }
+            auto load_x = [&](int it, F4(&v)[8], uint32_t &mask) {
+                const int kb = kb0 + it;
+                int off[2];
+                bool ok[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int m = kb * BLOCK_KP + r0 + 16 * h;
+                    const int yy = py[h] * p.stride + dyo, xx = px[h] * p.stride + dxo;
+                    ok[h] = m < p.M && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                    const int sy = UP ? (yy >> 1) : yy, sx = UP ? (xx >> 1) : xx;
+                    off[h] = ((pb[h] * p.Hs + sy) * p.Ws + sx) * xs + cb;
+                    px[h] += BLOCK_KP;
+                    while (px[h] >= p.Wout) {
+                        px[h] -= p.Wout;
+                        if (++py[h] == p.Hout) { py[h] = 0; ++pb[h]; }
+                    }
+                }
+                mask = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int h = i & 1, chunk = i >> 1;
+                    const int c = cb + chunk * 32;
+                    const bool live = chunk < nlive && ok[h] && c < p.Cin;
+                    if (VEC) {
+                        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) q4 = __ldg(reinterpret_cast<const float4 *>(xg + off[h] + chunk * 32));
+                        if (c + 3 >= p.Cin) {        // channel tail of a 16-byte-padded row
+                            if (c + 1 >= p.Cin) q4.y = 0.f;
+                            if (c + 2 >= p.Cin) q4.z = 0.f;
+                            q4.w = 0.f;
+                        }
+                        v[i].v[0] = q4.x; v[i].v[1] = q4.y; v[i].v[2] = q4.z; v[i].v[3] = q4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float q1 = 0.f;
+                            if (live && c + e < p.Cin) q1 = __ldg(xg + off[h] + chunk * 32 + e);
+                            v[i].v[e] = q1;
+                        }
+                    }
+                }
+            };
+            auto store_x = [&](int it, F4(&v)[8], uint32_t mask) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                if (PRE != 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float a = v[i].v[e];
+                            if (AFF) {
+                                a = fmaf(a, sc[i >> 1][e], sh[i >> 1][e]);
+                                if (RELU) a = fmaxf(a, 0.f);
+                                a = ((mask >> (i & 1)) & 1u) ? a : 0.f;
+                            } else {
+                                a = fmaxf(a, 0.f);
+                            }
+                            v[i].v[e] = a;
+                        }
+                }
+                mbar_wait(empty(s), ph ^ 1);
+                const uint32_t t_hi = base + s * Smem::STAGE_BYTES;
+                split_store(t_hi, t_hi + A_BYTES, v, nlive);
+                fence_proxy_async();
+                mbar_arrive(full(s));
+            };
+            F4 va[8], vb[8];
+            uint32_t ma = 0, mb = 0;
+            int it = 0;
+            if (it < nkb) load_x(it, va, ma);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load_x(it + 1, vb, mb);
+                store_x(it, va, ma);
+                if (more) {
+                    if (it + 2 < nkb) load_x(it + 2, va, ma);
+                    store_x(it + 1, vb, mb);
+                }
+            }
+        } else {
+            // ------------------------------ dY tiles (B operand): ceil(n_tile/32) chunks of output channels ------
+            const int dys = (int)p.dys;
+            const int nchunk = (n_tile + 31) >> 5;
+            const int cb = nt * n_tile + unit * 4;
+            const float *__restrict__ dg = p.dy;
+            auto load_d = [&](int it, F4(&v)[8]) {
+                const int kb = kb0 + it;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int h = i & 1, chunk = i >> 1;
+                    const int m = kb * BLOCK_KP + r0 + 16 * h;
+                    const int c = cb + chunk * 32;
+                    const bool live = chunk < nchunk && m < p.M && c < p.Cout;
+                    if (VEC) {
+                        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) q4 = __ldg(reinterpret_cast<const float4 *>(dg + m * dys + c));
+                        if (c + 3 >= p.Cout) {
+                            if (c + 1 >= p.Cout) q4.y = 0.f;
+                            if (c + 2 >= p.Cout) q4.z = 0.f;
+                            q4.w = 0.f;
+                        }
+                        v[i].v[0] = q4.x; v[i].v[1] = q4.y; v[i].v[2] = q4.z; v[i].v[3] = q4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float q1 = 0.f;
+                            if (live && c + e < p.Cout) q1 = __ldg(dg + m * dys + c + e);
+                            v[i].v[e] = q1;
+                        }
+                    }
+                }
+            };
+            auto store_d = [&](int it, F4(&v)[8]) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty(s), ph ^ 1);
+                const uint32_t t_hi = base + s * Smem::STAGE_BYTES + 2 * A_BYTES;
+                split_store(t_hi, t_hi + MAX_N * 128, v, nchunk);
+                fence_proxy_async();
+                mbar_arrive(full(s));
+            };
+            F4 va[8], vb[8];
+            int it = 0;
+            if (it < nkb) load_d(it, va);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load_d(it + 1, vb);
+                store_d(it, va);
+                if (more) {
+                    if (it + 2 < nkb) load_d(it + 2, va);
+                    store_d(it + 1, vb);
+                }
+            }
         }
-        for (int it = 0; it < nkb; ++it) {
-            const int j = it + ring - 1;
-            if (j < nkb) issue(j);
-            cp_async_commit();
-            cp_async_wait_dyn(ring - 1);
-            transform(it);
-        }
-        cp_async_wait_dyn(0);
 
         // ---- epilogue: TMEM lane = input channel, columns = output channels
         mbar_wait(accum_full, 0);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_conv_gpu.py -x -q 2>&1 | tail -6
+timeout 300 python tools/conv_layers.py fwd > gpurun_out/conv_layers_fwd4.log 2>&1; cat gpurun_out/conv_layers_fwd4.log
+timeout 300 python tools/conv_layers.py wgrad > gpurun_out/conv_layers_wgrad4.log 2>&1; tail -22 gpurun_out/conv_layers_wgrad4.log
