@@ -75,12 +75,31 @@ class Conv2dTC(nn.Conv2d):
         return torch.sigmoid(self.forward(x))
 
 
+def _dense_block_class():
+    from torchvision.models.densenet import _DenseBlock
+
+    class DenseBlockTC(_DenseBlock):
+        """torchvision dense block whose forward/backward run as ONE fused, concat-free autograd Function
+        (bts_b200/fused.py) when the tensor-core backend is active; identical parameters / buffers / state_dict."""
+
+        def forward(self, init_features):
+            from . import fused
+            if conv_backend() == "tc" and fused.dense_block_eligible(self, init_features):
+                return fused.dense_block_forward(self, init_features)
+            return super().forward(init_features)
+
+    return _DenseBlock, DenseBlockTC
+
+
 def adopt_convs(module):
-    """Re-class every eligible nn.Conv2d of a (torchvision) module tree to Conv2dTC in place -- parameter names,
-    shapes and init are untouched."""
+    """Re-class every eligible nn.Conv2d (-> Conv2dTC) and DenseNet block (-> fused DenseBlockTC) of a torchvision
+    module tree in place -- parameter names, shapes and init are untouched."""
+    base, fusedcls = _dense_block_class()
     for m in module.modules():
         if type(m) is nn.Conv2d:
             m.__class__ = Conv2dTC
+        elif type(m) is base:
+            m.__class__ = fusedcls
     return module
 
 

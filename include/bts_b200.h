@@ -135,6 +135,30 @@ int bts_conv_c1_wgrad(const float *x, long long x_pixel_stride, const float *dy,
                       int W, int C, int K, float *workspace, float *dw, long long s_ci, long long s_kh,
                       long long s_kw, void *stream);
 
+/* ---- train-mode BatchNorm pieces for fused BN -> ReLU -> conv chains (torchvision _DenseLayer norm1/relu1/conv1/
+ * norm2/relu2/conv2; decoder BNs bts.py:154-182).  The normalisation is applied inside the consumer conv
+ * (bts_conv_fwd pre_scale/pre_shift/pre_relu); these entry points provide the per-channel reductions and the
+ * backward pass over NHWC tensors (explicit pixel strides -> channel slices of slabs work in place).
+ *   bts_bn_stats            : sum / sum of squares per channel (fp64 accumulators, zeroed by the call)
+ *   bts_bn_finalize         : -> scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (+ running-stat update,
+ *                             momentum m, unbiased variance; running_* may be NULL)
+ *   bts_bn_fold             : the same four vectors from frozen running statistics (eval mode)
+ *   bts_bn_relu_bwd_reduce  : S1 = sum g*[y>0], S2 = sum g*[y>0]*xhat (y = x*scale+shift) and the fp32 backward
+ *                             coefficients coef[0:C] = k0, coef[C:2C] = k1 (dx = [y>0]*scale*g + k1*x + k0)
+ *   bts_bn_relu_bwd_apply   : out (=|+=) [y>0]*scale*g + k1*x + k0   (coef == NULL: frozen statistics, k0 = k1 = 0) */
+int bts_bn_stats(const float *x, long long x_pixel_stride, long long M, int C, double *sum, double *sumsq, void *stream);
+int bts_bn_finalize(const double *sum, const double *sumsq, long long N, int C, const float *gamma, const float *beta,
+                    float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                    float *mean, float *invstd, void *stream);
+int bts_bn_fold(int C, const float *gamma, const float *beta, float eps, const float *running_mean,
+                const float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream);
+int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                           long long M, int C, const float *scale, const float *shift, const float *mean,
+                           const float *invstd, double *S1, double *S2, float *coef, void *stream);
+int bts_bn_relu_bwd_apply(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                          long long M, int C, const float *scale, const float *shift, const float *coef, float *out,
+                          long long out_pixel_stride, int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
