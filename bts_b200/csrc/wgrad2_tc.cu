@@ -1,0 +1,428 @@
+// wgrad for narrow-output 3x3 convolutions (Cout <= 64: the DenseNet 3x3 dense-layer convs 192->48 and the full- /
+// half-resolution decoder convs conv1/upconv1/conv2/upconv2) on tcgen05 + TMEM, 3xTF32 -- "shifted dY" formulation.
+//
+//   dW[co, ci, tap] = sum_q  x~[q, ci] * dY[q - off(tap), co]            q = INPUT pixel, off(tap) = tap*dil - pad
+//
+// wgrad_tc.cu puts the tap in the grid, so the 128-channel activation tile -- the expensive operand: loads, BN/ReLU
+// pre-op, hi/lo split, 32 KB of shared-memory writes per k-block -- is produced 9 times, and with a narrow N the MMA
+// is too short to hide it (dense 3x3: 38 TF/s, conv1: 12 TF/s).  Here ONE CTA owns all taps of a (128 ci, <=48 co)
+// block: per k-block of 16 input pixels the activation tile is produced once and multiplied against the 9 shifted dY
+// tiles (cheap: <= 48 channels each), accumulating into 9 column blocks of TMEM (9 x 48 = 432 of 512 columns).
+// Same MN-major SWIZZLE_128B_BASE32B operand tiles and deterministic split-K partial layout as wgrad_tc.cu.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int BLOCK_CI = 128;
+constexpr int KP = 16;                       // input pixels per k-block (2 k-groups of 8)
+constexpr int CHUNK = KP * 128;              // one 32-channel chunk of a k-block: 2 KB
+constexpr int A_BYTES = 4 * CHUNK;           // 8 KB (hi or lo)
+constexpr int MAX_TAPS = 9;
+constexpr int MAX_STAGES = 4;
+constexpr int NUM_THREADS = 320;
+constexpr int SMEM_BUDGET = 224 * 1024;
+
+struct W2Params {
+    const float *x; long long xs;
+    int B, Hs, Ws, up, Cin;
+    int KH, KW, pad, dil;
+    const float *pre_scale, *pre_shift;
+    const float *dy; long long dys;
+    int Cout, Hout, Wout, Hin, Win;
+    int cg, nb;              // output channels per CTA (multiple of 16, <= 48) and their 32-channel chunks
+    float *part;             // [splitK][taps][Cin][Cout]
+    int splitK, kb_per_split, KBq;
+    int Mq;                  // B*Hin*Win input pixels
+    int stages, stage_bytes, precision;
+};
+
+template <int PRE, bool UP, bool VEC>
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+    const int taps = p.KH * p.KW;
+    const int S = p.stages;
+    const uint32_t pre_off = (uint32_t)S * (uint32_t)p.stage_bytes;
+    float *s_scale = reinterpret_cast<float *>(sm + pre_off);
+    float *s_shift = s_scale + BLOCK_CI;
+    const uint32_t bar0 = base + pre_off + 2 * BLOCK_CI * 4;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + pre_off + 2 * BLOCK_CI * 4);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    const uint32_t accum_full = bar0 + 8u * (2 * MAX_STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci_tile = blockIdx.x, cgi = blockIdx.y, split = blockIdx.z;
+    const int co0 = cgi * p.cg;
+    const int ncol = min(p.cg, ((p.Cout - co0 + 15) >> 4) << 4);     // live columns of this CTA (multiple of 16)
+    const int nb = p.nb;
+    const uint32_t b_tap = (uint32_t)nb * CHUNK;                     // bytes of one tap's dY tile (hi or lo)
+    const uint32_t b_half = (uint32_t)taps * b_tap;
+    const int kb0 = split * p.kb_per_split;
+    int kb1 = kb0 + p.kb_per_split;
+    if (kb1 > p.KBq) kb1 = p.KBq;
+    const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(full(s), 256);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (PRE >= 2) {
+        for (int c = threadIdx.x; c < BLOCK_CI; c += NUM_THREADS) {
+            const int ch = ci_tile * BLOCK_CI + c;
+            s_scale[c] = ch < p.Cin ? p.pre_scale[ch] : 0.f;
+            s_shift[c] = ch < p.Cin ? p.pre_shift[ch] : 0.f;
+        }
+    }
+    // zero every operand stage once: dead channel chunks / dead units are never written afterwards
+    for (int i = threadIdx.x; i < S * p.stage_bytes / 16; i += NUM_THREADS) st_shared_v4(base + i * 16, 0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BLOCK_CI, ncol, 1, 1);
+            const uint64_t dah0 = make_desc_mn(base, CHUNK), dal0 = make_desc_mn(base + A_BYTES, CHUNK);
+            const uint64_t dbh0 = make_desc_mn(base + 2 * A_BYTES, CHUNK), dbl0 = make_desc_mn(base + 2 * A_BYTES + b_half, CHUNK);
+            const uint64_t tap_step = (uint64_t)(b_tap >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint64_t so = (uint64_t)s * stage_step;
+#pragma unroll
+                for (int kg = 0; kg < KP / 8; ++kg) {
+                    const uint64_t o = so + (uint64_t)(kg * (1024 >> 4));   // start-address field: + 1024 B per k-group
+                    const uint32_t accumulate = (it | kg) != 0;
+                    uint64_t ob = o;
+                    uint32_t d = tmem_base;
+                    for (int t = 0; t < taps; ++t, ob += tap_step, d += (uint32_t)ncol) {
+                        if (p.precision == 0) {
+                            umma_tf32(d, dal0 + o, dbh0 + ob, idesc, accumulate);
+                            umma_tf32(d, dah0 + o, dbl0 + ob, idesc, 1);
+                            umma_tf32(d, dah0 + o, dbh0 + ob, idesc, 1);
+                        } else {
+                            umma_tf32(d, dah0 + o, dbh0 + ob, idesc, accumulate);
+                        }
+                    }
+                }
+                umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            umma_commit(accum_full);
+        }
+    } else if (warp >= 2) {
+        const int pt = threadIdx.x - 64;           // 0..255
+        const int unit = pt & 7;                   // 16-byte unit of the 128-byte row
+        const int row = (pt >> 3) & 15;            // pixel row of the 16-pixel k-block
+        const int half = pt >> 7;                  // A: chunks {2*half, 2*half+1};  dY: taps t == half (mod 2)
+        constexpr bool AFF = PRE >= 2;
+        constexpr bool RELU = (PRE & 1) != 0;
+        const uint32_t roff = mn_swizzle_off(row, unit);
+        const int xs = (int)p.xs, dys = (int)p.dys;
+        const int cbx = ci_tile * BLOCK_CI + half * 64 + unit * 4;    // first x channel of this thread (chunk 2*half)
+        const int cbd = co0 + unit * 4;                               // first dY channel (chunk 0)
+        const float *__restrict__ xg = p.x;
+        const float *__restrict__ dg = p.dy;
+        float sc[2][4], sh[2][4];
+        if (AFF) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sc[ch][e] = s_scale[half * 64 + ch * 32 + unit * 4 + e];
+                    sh[ch][e] = s_shift[half * 64 + ch * 32 + unit * 4 + e];
+                }
+        }
+        // input-pixel coordinates of this thread's row, advanced by 16 pixels per k-block (no divisions in the loop)
+        int qx, qy, qb;
+        {
+            const int q = kb0 * KP + row;
+            qx = q % p.Win;
+            const int r = q / p.Win;
+            qy = r % p.Hin;
+            qb = r / p.Hin;
+        }
+        constexpr int NBU = 10;                    // dY units per thread per k-block: <= 5 taps x 2 chunks
+        auto load = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool &okx) {
+            const int q = (kb0 + it) * KP + row;
+            okx = q < p.Mq;
+            // ---- x~ tile: this thread's pixel, channels of its two chunks
+            const int sy = UP ? (qy >> 1) : qy, sx = UP ? (qx >> 1) : qx;
+            const int xoff = ((qb * p.Hs + sy) * p.Ws + sx) * xs;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int c = cbx + ch * 32;
+                const bool live = okx && c < p.Cin;
+                if (VEC) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) v = __ldg(reinterpret_cast<const float4 *>(xg + xoff + c));
+                    if (c + 3 >= p.Cin) {
+                        if (c + 1 >= p.Cin) v.y = 0.f;
+                        if (c + 2 >= p.Cin) v.z = 0.f;
+                        v.w = 0.f;
+                    }
+                    va[ch].v[0] = v.x; va[ch].v[1] = v.y; va[ch].v[2] = v.z; va[ch].v[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v = 0.f;
+                        if (live && c + e < p.Cin) v = __ldg(xg + xoff + c + e);
+                        va[ch].v[e] = v;
+                    }
+                }
+            }
+            // ---- shifted dY tiles: taps t = half, half+2, ...; output pixel (qy - dy_t, qx - dx_t)
+#pragma unroll
+            for (int j = 0; j < NBU / 2; ++j) {
+                const int t = half + 2 * j;
+                const int ky = t / p.KW, kx = t - ky * p.KW;
+                const int py = qy - (ky * p.dil - p.pad), px = qx - (kx * p.dil - p.pad);
+                const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
+                const int doff = ((qb * p.Hout + py) * p.Wout + px) * dys;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int c = cbd + ch * 32;
+                    const bool live = okd && ch < nb && c < p.Cout && (c - co0) < ncol;
+                    F4 &dst = vb[j * 2 + ch];
+                    if (VEC) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) v = __ldg(reinterpret_cast<const float4 *>(dg + doff + c));
+                        if (c + 3 >= p.Cout) {
+                            if (c + 1 >= p.Cout) v.y = 0.f;
+                            if (c + 2 >= p.Cout) v.z = 0.f;
+                            v.w = 0.f;
+                        }
+                        dst.v[0] = v.x; dst.v[1] = v.y; dst.v[2] = v.z; dst.v[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float v = 0.f;
+                            if (live && c + e < p.Cout) v = __ldg(dg + doff + c + e);
+                            dst.v[e] = v;
+                        }
+                    }
+                }
+            }
+            qx += KP;
+            while (qx >= p.Win) {
+                qx -= p.Win;
+                if (++qy == p.Hin) { qy = 0; ++qb; }
+            }
+        };
+        auto split_store = [&](uint32_t hi_addr, uint32_t lo_addr, const F4 &v) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = v.v[e];
+                const float hh = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+                hi[e] = hh;
+                lo[e] = a - hh;
+            }
+            st_shared_v4(hi_addr, hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(lo_addr, lo[0], lo[1], lo[2], lo[3]);
+        };
+        auto store = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool okx) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1;
+            if (PRE != 0) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = va[ch].v[e];
+                        if (AFF) {
+                            a = fmaf(a, sc[ch][e], sh[ch][e]);
+                            if (RELU) a = fmaxf(a, 0.f);
+                            a = okx ? a : 0.f;
+                        } else {
+                            a = fmaxf(a, 0.f);
+                        }
+                        va[ch].v[e] = a;
+                    }
+            }
+            mbar_wait(empty(s), ph ^ 1);
+            const uint32_t a_hi = base + (uint32_t)s * (uint32_t)p.stage_bytes, a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_half;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const uint32_t o = (uint32_t)(half * 2 + ch) * CHUNK + roff;
+                split_store(a_hi + o, a_lo + o, va[ch]);
+            }
+#pragma unroll
+            for (int j = 0; j < NBU / 2; ++j) {
+                const int t = half + 2 * j;
+                if (t < taps) {
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch)
+                        if (ch < nb) {
+                            const uint32_t o = (uint32_t)t * b_tap + (uint32_t)ch * CHUNK + roff;
+                            split_store(b_hi + o, b_lo + o, vb[j * 2 + ch]);
+                        }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full(s));
+        };
+        {
+            F4 a0[2], a1[2], b0[NBU], b1[NBU];
+            bool k0 = false, k1 = false;
+            int it = 0;
+            if (it < nkb) load(it, a0, b0, k0);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load(it + 1, a1, b1, k1);
+                store(it, a0, b0, k0);
+                if (more) {
+                    if (it + 2 < nkb) load(it + 2, a0, b0, k0);
+                    store(it + 1, a1, b1, k1);
+                }
+            }
+        }
+
+        // ---- epilogue: TMEM lane = input channel; column block t*ncol.. = tap t; taps split between the two halves
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int q4 = warp & 3;
+        const int ci = ci_tile * BLOCK_CI + q4 * 32 + lane;
+        const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0) && ((co0 & 3) == 0);
+        for (int t = half; t < taps; t += 2) {
+            float *prow = p.part + (((long long)split * taps + t) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + co0;
+            for (int cc = 0; cc < ncol; cc += 8) {
+                uint32_t r[8];
+                tmem_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * ncol + cc), r);
+                tmem_ld_wait();
+                if (ci < p.Cin) {
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; e4 += 4) {
+                        const int c = co0 + cc + e4;
+                        if (ovec && c + 3 < p.Cout) {
+                            *reinterpret_cast<float4 *>(prow + cc + e4) =
+                                make_float4(nkb ? __uint_as_float(r[e4]) : 0.f, nkb ? __uint_as_float(r[e4 + 1]) : 0.f,
+                                            nkb ? __uint_as_float(r[e4 + 2]) : 0.f, nkb ? __uint_as_float(r[e4 + 3]) : 0.f);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c + e < p.Cout) prow[cc + e4 + e] = nkb ? __uint_as_float(r[e4 + e]) : 0.f;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// co-group width for the shifted-dY kernel: multiple of 16, taps*cg <= 512 TMEM columns, groups as even as possible
+int bts_wgrad2_cg(int Cout, int taps) {
+    int cap = (512 / taps) / 16 * 16;
+    if (cap > 48) cap = 48;
+    if (cap < 16) return 0;
+    const int groups = (Cout + cap - 1) / cap;
+    int cg = ((Cout + groups - 1) / groups + 15) / 16 * 16;
+    if (cg > cap) cg = cap;
+    return cg;
+}
+
+// measured (B200, K16 shapes): wins for Cout <= 48 on maps of >= 60k pixels (dense 3x3 of blocks 1-2, conv1, upconv1);
+// loses for Cout = 64 (two co groups re-produce the activation tile) and on the small maps of blocks 3-4
+bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq) {
+    const int taps = KH * KW;
+    return taps > 1 && taps <= MAX_TAPS && Cout <= 48 && stride == 1 && Mq >= 60000 && bts_wgrad2_cg(Cout, taps) > 0;
+}
+
+void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK) {
+    const int taps = KH * KW;
+    const int cg = bts_wgrad2_cg(Cout, taps);
+    const long long Mq = (long long)B * Hin * Win;
+    const long long KBq = (Mq + KP - 1) / KP;
+    const long long tiles = (long long)((Cin + BLOCK_CI - 1) / BLOCK_CI) * ((Cout + cg - 1) / cg);
+    const int sms = bts_num_sms();
+    long long max_split = (KBq + 31) / 32;
+    if (max_split < 1) max_split = 1;
+    if (max_split > 512) max_split = 512;
+    long long split = 1;
+    double best = -1.0;
+    for (long long sp = 1; sp <= max_split; ++sp) {
+        const long long ctas = tiles * sp;
+        const long long waves = (ctas + sms - 1) / sms;
+        if (waves > 2 && sp > 1) break;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff >= best - 1e-9) { best = eff; split = sp; }
+    }
+    *splitK = (int)split;
+}
+
+int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int up, int Cin, int KH, int KW, int pad,
+                      int dil, const float *pre_scale, const float *pre_shift, int pre_relu, const float *dy,
+                      long long dys, int Cout, int Hout, int Wout, float *workspace, int splitK, int precision,
+                      cudaStream_t st) {
+    W2Params p;
+    const int taps = KH * KW;
+    p.x = x; p.xs = xs; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = up; p.Cin = Cin;
+    p.KH = KH; p.KW = KW; p.pad = pad; p.dil = dil;
+    p.pre_scale = pre_scale; p.pre_shift = pre_shift;
+    p.dy = dy; p.dys = dys; p.Cout = Cout; p.Hout = Hout; p.Wout = Wout;
+    p.Hin = up ? 2 * Hs : Hs; p.Win = up ? 2 * Ws : Ws;
+    p.cg = bts_wgrad2_cg(Cout, taps);
+    p.nb = (p.cg + 31) / 32;
+    p.part = workspace; p.splitK = splitK;
+    const long long Mq = (long long)B * p.Hin * p.Win;
+    if (Mq > 0x7ffffff0LL) return BTS_EINVAL;
+    p.Mq = (int)Mq;
+    p.KBq = (int)((Mq + KP - 1) / KP);
+    p.kb_per_split = (p.KBq + splitK - 1) / splitK;
+    p.stage_bytes = 2 * A_BYTES + 2 * taps * p.nb * CHUNK;
+    p.stages = SMEM_BUDGET / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    if (p.stages < 2) return BTS_EINVAL;
+    p.precision = precision;
+    const int smem = p.stages * p.stage_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
+    dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.cg - 1) / p.cg, splitK);
+    const int pre = (pre_scale ? 2 : 0) | (pre_relu ? 1 : 0);
+    const bool vec = bts_aligned16(x) && (xs % 4 == 0) && bts_aligned16(dy) && (dys % 4 == 0);
+    cudaError_t err = cudaSuccess;
+#define BTS_LAUNCH(PRE, UP, VEC)                                                                                      \
+    do {                                                                                                              \
+        static int attr_smem = 0;                                                                                     \
+        if (attr_smem < smem) {                                                                                       \
+            err = cudaFuncSetAttribute(wgrad2_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       SMEM_BUDGET + 2 * BLOCK_CI * 4 + 256 + 1024);                                  \
+            if (err != cudaSuccess) return (int)err;                                                                  \
+            attr_smem = SMEM_BUDGET + 2 * BLOCK_CI * 4 + 256 + 1024;                                                  \
+        }                                                                                                             \
+        wgrad2_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, smem, st>>>(p);                                           \
+    } while (0)
+#define BTS_DISPATCH_UV(PRE)                                                                     \
+    do {                                                                                         \
+        if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true); else BTS_LAUNCH(PRE, true, false); }   \
+        else { if (vec) BTS_LAUNCH(PRE, false, true); else BTS_LAUNCH(PRE, false, false); }      \
+    } while (0)
+    switch (pre) {
+        case 0: BTS_DISPATCH_UV(0); break;
+        case 1: BTS_DISPATCH_UV(1); break;
+        case 2: BTS_DISPATCH_UV(2); break;
+        default: BTS_DISPATCH_UV(3); break;
+    }
+#undef BTS_DISPATCH_UV
+#undef BTS_LAUNCH
+    BTS_LAUNCH_CHECK();
+    return 0;
+}

@@ -373,9 +373,24 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 
 extern "C" int bts_conv_n_tile(int Cout);
 
+// narrow-output 3x3 layers use the shifted-dY kernel (wgrad2_tc.cu)
+bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq);
+void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK);
+int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int up, int Cin, int KH, int KW, int pad,
+                      int dil, const float *pre_scale, const float *pre_shift, int pre_relu, const float *dy,
+                      long long dys, int Cout, int Hout, int Wout, float *workspace, int splitK, int precision,
+                      cudaStream_t st);
+
 extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int *splitK_out,
                                    long long *workspace_floats) {
     if (!splitK_out || !workspace_floats || B < 1 || Hout < 1 || Wout < 1 || Cin < 1 || Cout < 1) return BTS_EINVAL;
+    if (bts_wgrad2_eligible(Cout, KH, KW, 1, (long long)B * Hout * Wout)) {
+        int sp = 1;
+        bts_wgrad2_plan(B, Hout, Wout, Cin, Cout, KH, KW, &sp);
+        *splitK_out = sp;
+        *workspace_floats = (long long)sp * KH * KW * (long long)Cin * Cout;
+        return 0;
+    }
     const long long M = (long long)B * Hout * Wout;
     const long long KBp = (M + BLOCK_KP - 1) / BLOCK_KP;
     const int n_tile = bts_conv_n_tile(Cout);
@@ -429,6 +444,20 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     p.dy_vec = bts_aligned16(dy) && (dy_pixel_stride % 4 == 0);
     p.precision = precision;
     const int taps = KH * KW;
+    if (bts_wgrad2_eligible(Cout, KH, KW, stride, M)) {
+        int rc2 = bts_wgrad2_launch(x, x_pixel_stride, B, Hs, Ws, p.up, Cin, KH, KW, pad, dil, pre_scale, pre_shift,
+                                    p.pre_relu, dy, dy_pixel_stride, Cout, p.Hout, p.Wout, workspace, splitK, precision,
+                                    (cudaStream_t)stream);
+        if (rc2) return rc2;
+        const long long per2 = (long long)taps * Cin * Cout;
+        long long g2 = (per2 + 255) / 256;
+        const long long cap2 = (long long)bts_num_sms() * 16;
+        if (g2 > cap2) g2 = cap2;
+        wgrad_reduce_kernel<<<(int)g2, 256, 0, (cudaStream_t)stream>>>(workspace, splitK, taps, Cin, Cout, KW, dw, s_co, s_ci,
+                                                                      s_kh, s_kw);
+        BTS_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.n_tile - 1) / p.n_tile, taps * splitK);
     if (grid.z > 65535) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;

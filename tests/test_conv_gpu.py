@@ -136,3 +136,32 @@ def test_single_output_channel_head_kernels(C, K, sig):
     assert (y.detach().cpu().double() - yd.detach()).abs().max() < 1e-5
     assert (xc.grad.cpu().double() - xd.grad).abs().max() / xd.grad.abs().max() < 1e-5
     assert (wc.grad.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,dil,up,pre", [(192, 48, 9, 11, 1, False, True), (36, 32, 10, 13, 1, False, False),
+                                                     (64, 32, 6, 7, 1, True, False), (161, 64, 8, 9, 1, False, False),
+                                                     (40, 24, 7, 5, 3, False, True)])
+def test_wgrad_narrow_output_shifted_dy_kernel(Cin, Cout, H, W, dil, up, pre):
+    """Cout <= 64, 3x3: the all-taps-in-one-CTA wgrad (wgrad2_tc.cu) incl. fused BN+ReLU prologue, nearest-x2
+    up-sampling, dilation, odd channel counts (scalar-load path) -- vs torch fp64 autograd."""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(2, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g) * 0.3
+    Ho, Wo = (2 * H, 2 * W) if up else (H, W)
+    gy = torch.randn(2, Cout, Ho, Wo, generator=g)
+    xd = x.double()
+    if pre:
+        xd = F.relu(xd * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+    if up:
+        xd = F.interpolate(xd, scale_factor=2, mode="nearest")
+    wd = w.double().requires_grad_(True)
+    F.conv2d(xd, wd, None, 1, dil, dil).backward(gy.double())
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    gw = conv.wgrad_tc(xc, gy.cuda().contiguous(memory_format=torch.channels_last), w.shape, w.stride(), 1, dil, dil,
+                       pre_scale=sc.cuda() if pre else None, pre_shift=sh.cuda() if pre else None, pre_relu=pre,
+                       upsample2=up)
+    err = (gw.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max()
+    assert err < 2e-5, err
