@@ -89,6 +89,15 @@ SIGNATURES = {
     "bts_bn_fold": [_i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _i, _p],
+    "bts_bn_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],
+    "bts_bn_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _i, _p, _ll, _i, _p],
+    "bts_bn_apply": [_p, _ll, _ll, _i, _p, _p, _i, _p, _ll, _p],
+    "bts_elu_bwd": [_p, _ll, _p, _ll, _ll, _i, _p, _ll, _p],
+    "bts_upsample2_sum": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p, _ll, _p],
+    "bts_copy_channels": [_p, _ll, _ll, _i, _p, _ll, _i, _p],
+    "bts_zero_channels": [_p, _ll, _ll, _i, _i, _p],
+    "bts_avgpool2_fwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
+    "bts_avgpool2_bwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
 }
 RESTYPES = {"bts_conv_packed_floats": ctypes.c_longlong}
 

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float *__restrict_
                                                         long long gs, long long M, int C, int rows,
                                                         const float *__restrict__ scale, const float *__restrict__ shift,
                                                         const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                        double *__restrict__ acc0, double *__restrict__ acc1) {
+                                                        double *__restrict__ acc0, double *__restrict__ acc1, int relu) {
     __shared__ float red[2][256 * 4];
     const int cchunk = min(256, C - (int)blockIdx.y * 256);
     const int tpc = (cchunk + 3) >> 2;                 // threads per pixel row
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float *__restrict_
                     a1[e] = fmaf(xv[e], xv[e], a1[e]);
                 } else {
                     const float y = fmaf(xv[e], sc[e], sh[e]);
-                    const float gm = y > 0.f ? gv[e] : 0.f;
+                    const float gm = (!relu || y > 0.f) ? gv[e] : 0.f;
                     a0[e] += gm;
                     a1[e] = fmaf(gm, (xv[e] - mu[e]) * is[e], a1[e]);
                 }
@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float *__r
                                                                 const float *__restrict__ g, long long gs, long long M,
                                                                 int C, const float *__restrict__ scale,
                                                                 const float *__restrict__ shift, const float *__restrict__ coef,
-                                                                float *__restrict__ out, long long os, int accumulate) {
+                                                                float *__restrict__ out, long long os, int accumulate,
+                                                                int relu) {
     const int cq = (C + 3) >> 2;
     const long long total = M * cq;
     const bool vec = ((xs & 3) == 0) && ((gs & 3) == 0) && ((os & 3) == 0) && ((((uintptr_t)x) & 15) == 0) &&
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float *__r
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float y = fmaf(xv[e], sc[e], sh[e]);
-            float d = y > 0.f ? sc[e] * gv[e] : 0.f;
+            float d = (!relu || y > 0.f) ? sc[e] * gv[e] : 0.f;
             d += fmaf(xv[e], k1[e], k0[e]);
             r[e] = ov[e] + d;
         }
@@ -260,7 +261,7 @@ extern "C" int bts_bn_stats(const float *x, long long x_pixel_stride, long long 
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
     bn_reduce_kernel<false><<<grid, 256, 0, st>>>(x, x_pixel_stride, nullptr, 0, M, C, rows, nullptr, nullptr, nullptr,
-                                                  nullptr, sum, sumsq);
+                                                  nullptr, sum, sumsq, 0);
     BTS_LAUNCH_CHECK();
     return 0;
 }
@@ -284,9 +285,9 @@ extern "C" int bts_bn_fold(int C, const float *gamma, const float *beta, float e
     return 0;
 }
 
-extern "C" int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
-                                      long long M, int C, const float *scale, const float *shift, const float *mean,
-                                      const float *invstd, double *S1, double *S2, float *coef, void *stream) {
+extern "C" int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                                 long long M, int C, const float *scale, const float *shift, const float *mean,
+                                 const float *invstd, int relu, double *S1, double *S2, float *coef, void *stream) {
     if (!x || !g || !scale || !shift || !mean || !invstd || !S1 || !S2 || !coef || M < 1 || C < 1) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -296,9 +297,30 @@ extern "C" int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, 
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
     bn_reduce_kernel<true><<<grid, 256, 0, st>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, rows, scale, shift, mean, invstd,
-                                                 S1, S2);
+                                                 S1, S2, relu);
     BTS_LAUNCH_CHECK();
     bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(S1, S2, M, C, scale, mean, invstd, coef);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                                      long long M, int C, const float *scale, const float *shift, const float *mean,
+                                      const float *invstd, double *S1, double *S2, float *coef, void *stream) {
+    return bts_bn_bwd_reduce(x, x_pixel_stride, g, g_pixel_stride, M, C, scale, shift, mean, invstd, 1, S1, S2, coef, stream);
+}
+
+extern "C" int bts_bn_bwd_apply(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                                long long M, int C, const float *scale, const float *shift, const float *coef, int relu,
+                                float *out, long long out_pixel_stride, int accumulate, void *stream) {
+    if (!x || !g || !scale || !shift || !out || M < 1 || C < 1) return BTS_EINVAL;
+    const long long total = M * ((C + 3) / 4);
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    bn_relu_bwd_apply_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, scale,
+                                                                          shift, coef, out, out_pixel_stride, accumulate,
+                                                                          relu);
     BTS_LAUNCH_CHECK();
     return 0;
 }
@@ -306,13 +328,6 @@ extern "C" int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, 
 extern "C" int bts_bn_relu_bwd_apply(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
                                      long long M, int C, const float *scale, const float *shift, const float *coef,
                                      float *out, long long out_pixel_stride, int accumulate, void *stream) {
-    if (!x || !g || !scale || !shift || !out || M < 1 || C < 1) return BTS_EINVAL;
-    const long long total = M * ((C + 3) / 4);
-    long long grid = (total + 255) / 256;
-    const long long cap = (long long)bts_num_sms() * 16;
-    if (grid > cap) grid = cap;
-    bn_relu_bwd_apply_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, scale,
-                                                                          shift, coef, out, out_pixel_stride, accumulate);
-    BTS_LAUNCH_CHECK();
-    return 0;
+    return bts_bn_bwd_apply(x, x_pixel_stride, g, g_pixel_stride, M, C, scale, shift, coef, 1, out, out_pixel_stride,
+                            accumulate, stream);
 }

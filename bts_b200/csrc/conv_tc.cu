@@ -37,11 +37,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // fp32 elements per k-block = one 128-byte row
 constexpr int MAX_N = 128;
-constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB (hi or lo)
 constexpr int NUM_THREADS = 448;
 constexpr int PRODUCER_THREADS = 128;       // per group
-constexpr int MAX_CIN_SMEM = 4096;          // pre-op scale/shift staged in smem
+constexpr int MAX_CIN_SMEM = 4096;          // pre-op scale/shift staged in smem (32 KB at most)
 constexpr int EPI_THREADS = 128;
 constexpr int TMEM_COLS = 256;              // two 128-column fp32 accumulators
 
@@ -67,6 +66,8 @@ struct ConvParams {
     int m_tiles, total_tiles;
     int KC;                  // ceil(Cin/32)
     int KB;                  // KH*KW*KC k-blocks
+    int stages, stage_bytes; // smem ring: as many (A hi/lo + B hi/lo) stages as fit
+    tc::FastDiv fd_wout, fd_hout, fd_ntiles;
 };
 
 using namespace tc;
@@ -117,34 +118,46 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------------------------------- main kernel
-struct SmemLayout {
-    // dynamic smem, 1024-byte aligned base:
-    //   [STAGES][A_hi 16K | A_lo 16K | B_hi n_tile*128 | B_lo n_tile*128]   (B region sized for MAX_N)
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * MAX_N * 128;   // 64 KB
-    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;                      // scale[MAX_CIN_SMEM], shift[...]
-    static constexpr int BAR_OFF = PRE_OFF + 2 * MAX_CIN_SMEM * 4;
-    static constexpr int TOTAL = BAR_OFF + 256;
-};
+// dynamic smem, 1024-byte aligned base:
+//   [S stages][A_hi 16K | A_lo 16K | B_hi n_tile*128 | B_lo n_tile*128]   S = as many stages as fit (2..MAX_STAGES)
+//   [pre-op scale[KC*32], shift[KC*32]]  (PRE >= 2 only)   [mbarriers]
+// Narrow-N layers (n_tile <= 64: the DenseNet 3x3 convs, the full-resolution decoder convs, most dgrads) get 4-5
+// stages instead of 3: with two producer groups alternating k-blocks, 3 stages left each group at most one stage of
+// slack and the ncu samples showed the producers parked on `empty` 23 % of the time.
+constexpr int MAX_STAGES = 6;
+constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
+constexpr int BAR_BYTES = 256;
 
 // PRE: 0 none, 1 ReLU, 2 affine, 3 affine + ReLU (compile-time so the per-element producer code carries no dead ops)
 // UP : nearest x2 up-sample folded into the address map;  VEC: 16-byte aligned rows (float4 loads)
+//
+// Index arithmetic (ncu, round 1: 84 % of the executed instructions were integer division sequences, predicate /
+// address recomputation and mbarrier spin loops -- each producer warp issued one instruction every ~9 cycles):
+//   * every k-block -> (tile, tap, channel chunk, stage, phase) mapping is carried in incrementally updated counters;
+//   * the per-tile pixel decode uses multiply-shift division by host-precomputed constants (FastDiv);
+//   * long waits (epilogue on the accumulator, weight loader on a free stage) back off with nanosleep so the spinning
+//     warps stop competing with the producers for issue slots.
 template <int PRE, bool UP, bool VEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
-    float *s_scale = reinterpret_cast<float *>(sm + SmemLayout::PRE_OFF);
-    float *s_shift = s_scale + MAX_CIN_SMEM;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SmemLayout::BAR_OFF);
-    // bars: [0..S) full_a, [S..2S) full_b, [2S..3S) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base word
-    const uint32_t bar0 = base + SmemLayout::BAR_OFF;
+    const int S = p.stages;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    const uint32_t pre_off = (uint32_t)S * stage_bytes;
+    float *s_scale = reinterpret_cast<float *>(sm + pre_off);
+    float *s_shift = s_scale + p.KC * 32;
+    const uint32_t bar_off = pre_off + (PRE >= 2 ? (uint32_t)p.KC * 32u * 8u : 0u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + bar_off);
+    // bars: [0..MS) full_a, [MS..2MS) full_b, [2MS..3MS) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base word
+    const uint32_t bar0 = base + bar_off;
     auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    auto tmem_full = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
-    auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 4);
+    auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+    auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
+    auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = p.n_tile;
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     const int total_kb = my_tiles * KB;          // host guarantees < 2^31
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(full_a(s), PRODUCER_THREADS);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
@@ -181,17 +194,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ===================== weight loader =====================
         if (lane == 0) {
             const uint32_t bytes = 2u * (uint32_t)n_tile * 128u;
-            int gk = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int nt = tile % p.n_tiles;
+                const int nt = tile - (int)fdiv((uint32_t)tile, p.fd_ntiles) * p.n_tiles;
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * bytes;
-                for (int kb = 0; kb < KB; ++kb, ++gk) {
-                    const int s = gk % STAGES;
-                    const uint32_t ph = (uint32_t)(gk / STAGES) & 1;
-                    mbar_wait(empty(s), ph ^ 1);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait_sleep(empty(s), ph ^ 1);
                     mbar_arrive_expect_tx(full_b(s), bytes);
-                    bulk_copy_g2s(base + s * SmemLayout::STAGE_BYTES + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
+                    bulk_copy_g2s(base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -199,19 +212,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
-            int gk = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
                 mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb, ++gk) {
-                    const int s = gk % STAGES;
-                    const uint32_t ph = (uint32_t)(gk / STAGES) & 1;
+                for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(full_a(s), ph);
                     mbar_wait(full_b(s), ph);
                     tc_fence_after();
-                    const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
+                    const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
                     const uint32_t a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
                     const uint32_t b_lo = b_hi + n_tile * 128;
@@ -230,6 +242,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                             umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(empty(s));       // frees the stage when these MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tmem_full(acc));     // accumulator of this tile complete
             }
@@ -240,38 +253,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int grp = pt >> 7;                   // producer group: global k-blocks gk == grp (mod 2)
         const int t = pt & 127;
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
-        const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7
+        const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7  (row & 7 == r0 & 7 for all of them)
         const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
         const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
+        const int KC = p.KC, KW = p.KW, KH = p.KH, dil = p.dil, Cin = p.Cin, Ws = p.Ws;
         constexpr bool AFF = PRE >= 2;
         constexpr bool RELU = (PRE & 1) != 0;
         const float *__restrict__ xg = p.x;
-        uint32_t roff[8];                          // swizzled byte offset of (row, chunk) inside a tile
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = r0 + 16 * i;
-            roff[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        }
-        // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block to load, with the per-row output
-        //      pixel origin of that tile in input coordinates
+        // swizzled byte offset of (row r0 + 16 i, chunk) inside a tile = roff0 + i * 2048
+        const uint32_t roff0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);
+        const int c0 = chunk * 4;
+        // ---- LOAD cursor: (tile iteration, tap row/col, channel chunk) of the next k-block this group loads
         int oy[8], ox[8], rowoff[8];
-        int l_ti = -1;
-        int l_gk = grp;
+        int l_ti = 0, l_ky = 0, l_kx = 0, l_kc = 0, cur_ti = -1;
+        auto advance = [&]() {
+            if (++l_kc == KC) {
+                l_kc = 0;
+                if (++l_kx == KW) {
+                    l_kx = 0;
+                    if (++l_ky == KH) { l_ky = 0; ++l_ti; }
+                }
+            }
+        };
+        if (grp) advance();
         auto set_tile = [&](int ti) {
-            l_ti = ti;
+            cur_ti = ti;
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-            const int m_tile = tile / p.n_tiles;
+            const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntiles);
+            const uint32_t m_base = m_tile * BLOCK_M + (uint32_t)r0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const long long m = (long long)m_tile * BLOCK_M + r0 + 16 * i;
-                if (m < p.M) {
-                    const int x = (int)(m % p.Wout);
-                    const int q = (int)(m / p.Wout);
-                    const int y = q % p.Hout;
-                    const int b = q / p.Hout;
+                const uint32_t m = m_base + 16u * i;
+                if ((long long)m < p.M) {
+                    const uint32_t q = fdiv(m, p.fd_wout);
+                    const int x = (int)(m - q * (uint32_t)p.Wout);
+                    const uint32_t b = fdiv(q, p.fd_hout);
+                    const int y = (int)(q - b * (uint32_t)p.Hout);
                     oy[i] = y * p.stride - p.pad;
                     ox[i] = x * p.stride - p.pad;
-                    rowoff[i] = b * p.Hs * p.Ws * xs + (UP ? 0 : (oy[i] * p.Ws + ox[i]) * xs);
+                    rowoff[i] = (int)b * p.Hs * Ws * xs + (UP ? 0 : (oy[i] * Ws + ox[i]) * xs);
                 } else {
                     oy[i] = ox[i] = -0x40000000;   // never in bounds
                     rowoff[i] = 0;
@@ -280,22 +300,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         };
         // ---- load phase: this lane's 8 x 16-byte global loads of one k-block (predicated, branch-free)
         auto load_kb = [&](F4(&v)[8], uint32_t &mask) {
-            const int ti = l_gk / KB;
-            const int kb = l_gk - ti * KB;
-            if (ti != l_ti) set_tile(ti);
-            const int tap = kb / p.KC, kc = kb - tap * p.KC;
-            const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            const int dy = ky * p.dil, dx = kx * p.dil;
-            const int c = kc * 32 + chunk * 4;     // first channel of this lane's 16-byte unit
-            const int tapoff = UP ? 0 : (dy * p.Ws + dx) * xs + c;
+            if (l_ti != cur_ti) set_tile(l_ti);
+            const int dy = l_ky * dil, dx = l_kx * dil;
+            const int c = l_kc * 32 + c0;          // first channel of this lane's 16-byte unit
+            const bool cok = c < Cin;
+            const int tapoff = UP ? c : (dy * Ws + dx) * xs + c;
             uint32_t mk = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int yy = oy[i] + dy, xx = ox[i] + dx;
-                const bool ok = (c < p.Cin) && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                const bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
                 mk |= (ok ? 1u : 0u) << i;
                 int off;
-                if (UP) off = rowoff[i] + ((yy >> 1) * p.Ws + (xx >> 1)) * xs + c;
+                if (UP) off = rowoff[i] + ((yy >> 1) * Ws + (xx >> 1)) * xs + tapoff;
                 else off = rowoff[i] + tapoff;
                 if (VEC) {
                     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -305,50 +322,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float q = 0.f;
-                        if (ok && c + e < p.Cin) q = __ldg(xg + off + e);
+                        if (ok && c + e < Cin) q = __ldg(xg + off + e);
                         v[i].v[e] = q;
                     }
                 }
             }
             mask = mk;
-            l_gk += 2;
+            advance();
+            advance();
         };
         // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
         //      hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is
         //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
-        int s_gk = grp;
+        int s_s = grp;                             // stage of this group's next store (S >= 2)
+        uint32_t s_ph = 0;
+        int s_kc = grp;
+        while (s_kc >= KC) s_kc -= KC;
         auto store_kb = [&](F4(&v)[8], uint32_t mask) {
-            const int s = s_gk % STAGES;
-            const uint32_t ph = (uint32_t)(s_gk / STAGES) & 1;
-            const int kb = s_gk % KB;
-            const int c = (kb % p.KC) * 32 + chunk * 4;
-            s_gk += 2;
-            mbar_wait(empty(s), ph ^ 1);
-            const uint32_t a_hi = base + s * SmemLayout::STAGE_BYTES;
+            const int c = s_kc * 32 + c0;
+            const uint32_t a_hi = base + (uint32_t)s_s * stage_bytes + roff0;
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t bar_full = full_a(s_s);
+            mbar_wait(empty(s_s), s_ph ^ 1);
+            s_s += 2;
+            if (s_s >= S) { s_s -= S; s_ph ^= 1; }
+            s_kc += 2;
+            while (s_kc >= KC) s_kc -= KC;
             float sc[4], sh[4];
             if (AFF) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { sc[e] = s_scale[c + e]; sh[e] = s_shift[c + e]; }
+                const float4 a4 = *reinterpret_cast<const float4 *>(s_scale + c);
+                const float4 b4 = *reinterpret_cast<const float4 *>(s_shift + c);
+                sc[0] = a4.x; sc[1] = a4.y; sc[2] = a4.z; sc[3] = a4.w;
+                sh[0] = b4.x; sh[1] = b4.y; sh[2] = b4.z; sh[3] = b4.w;
             }
-            if (VEC && c < p.Cin && c + 3 >= p.Cin) {
+            if (VEC && c < Cin && c + 3 >= Cin) {
                 // channel tail (Cin % 4 != 0, rows padded to 16 B): the float4 read past Cin -- zero those lanes
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int e = 1; e < 4; ++e)
-                        if (c + e >= p.Cin) v[i].v[e] = 0.f;
+                        if (c + e >= Cin) v[i].v[e] = 0.f;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float hi[4], lo[4];
+                const bool live = (mask >> i) & 1u;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float a = v[i].v[e];
                     if (AFF) {
                         a = fmaf(a, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
                         if (RELU) a = fmaxf(a, 0.f);
-                        a = ((mask >> i) & 1u) ? a : 0.f;       // zero padding is applied after the pre-op
+                        a = live ? a : 0.f;                     // zero padding is applied after the pre-op
                     } else if (RELU) {
                         a = fmaxf(a, 0.f);                      // padded lanes were loaded as 0
                     }
@@ -356,11 +381,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     hi[e] = h;
                     lo[e] = a - h;
                 }
-                st_shared_v4(a_hi + roff[i], hi[0], hi[1], hi[2], hi[3]);
-                st_shared_v4(a_lo + roff[i], lo[0], lo[1], lo[2], lo[3]);
+                st_shared_v4(a_hi + (uint32_t)i * 2048u, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + (uint32_t)i * 2048u, lo[0], lo[1], lo[2], lo[3]);
             }
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
-            mbar_arrive(full_a(s));
+            mbar_arrive(bar_full);
         };
         // ---- software pipeline (register ping-pong): the loads of this group's next k-block -- possibly of the next
         //      tile -- are in flight while the current one is transformed and stored
@@ -386,11 +411,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0);
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-            const int m_tile = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int m_tile = (int)fdiv((uint32_t)tile, p.fd_ntiles), nt = tile - m_tile * p.n_tiles;
             const int acc = ti & 1;
             const long long m = (long long)m_tile * BLOCK_M + row;
             float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
-            mbar_wait(tmem_full(acc), (uint32_t)((ti >> 1) & 1));
+            mbar_wait_sleep(tmem_full(acc), (uint32_t)((ti >> 1) & 1));
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
             for (int cc = 0; cc < n_tile; cc += 16) {
@@ -496,12 +521,22 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     p.KB = KH * KW * p.KC;
     p.vec_ok = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
     const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-    if (m_tiles * p.n_tiles * (long long)p.KB > 0x7fffffffLL) return BTS_EINVAL;
+    if (m_tiles * p.n_tiles * (long long)p.KB > 0x7fffffffLL || p.M + BLOCK_M >= 0x7fffffffLL) return BTS_EINVAL;
     p.m_tiles = (int)m_tiles;
     p.total_tiles = (int)(m_tiles * p.n_tiles);
+    p.fd_wout = make_fastdiv((uint32_t)p.Wout);
+    p.fd_hout = make_fastdiv((uint32_t)p.Hout);
+    p.fd_ntiles = make_fastdiv((uint32_t)p.n_tiles);
+    const int pre = (pre_scale ? 2 : 0) | (p.pre_relu ? 1 : 0);
+    // shared-memory plan: stage = A hi/lo (2 x 16 KB) + B hi/lo (2 x n_tile x 128 B); as many stages as fit
+    p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.n_tile * 128;
+    const int pre_bytes = pre >= 2 ? p.KC * 32 * 8 : 0;
+    p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes) / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    if (p.stages < 2) return BTS_EINVAL;
+    const int smem = p.stages * p.stage_bytes + pre_bytes + BAR_BYTES + 1024;
     const int sms = bts_num_sms();
     dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
-    const int pre = (pre_scale ? 2 : 0) | (p.pre_relu ? 1 : 0);
     const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
     cudaError_t err = cudaSuccess;
 #define BTS_LAUNCH(PRE, UP, VEC)                                                                                   \
@@ -509,11 +544,11 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
         static bool attr_set = false;                                                                              \
         if (!attr_set) {                                                                                           \
             err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                       SmemLayout::TOTAL + 1024);                                                  \
+                                       SMEM_LIMIT);                                                                \
             if (err != cudaSuccess) return (int)err;                                                               \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        conv_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, SmemLayout::TOTAL + 1024, (cudaStream_t)stream>>>(p);    \
+        conv_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);                        \
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                  \
     do {                                                      \

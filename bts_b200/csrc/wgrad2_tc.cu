@@ -157,6 +157,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             qb = r / p.Hin;
         }
         constexpr int NBU = 10;                    // dY units per thread per k-block: <= 5 taps x 2 chunks
+        // tap offsets of this thread's taps (t = half, half+2, ...), computed once: no divisions in the k-loop
+        int toy[NBU / 2], tox[NBU / 2];
+#pragma unroll
+        for (int j = 0; j < NBU / 2; ++j) {
+            const int t = half + 2 * j;
+            const int ky = t / p.KW, kx = t - ky * p.KW;
+            toy[j] = ky * p.dil - p.pad;
+            tox[j] = kx * p.dil - p.pad;
+        }
         auto load = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool &okx) {
             const int q = (kb0 + it) * KP + row;
             okx = q < p.Mq;
@@ -189,8 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
                 const int t = half + 2 * j;
-                const int ky = t / p.KW, kx = t - ky * p.KW;
-                const int py = qy - (ky * p.dil - p.pad), px = qx - (kx * p.dil - p.pad);
+                const int py = qy - toy[j], px = qx - tox[j];
                 const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
                 const int doff = ((qb * p.Hout + py) * p.Wout + px) * dys;
 #pragma unroll
@@ -235,9 +243,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             st_shared_v4(hi_addr, hi[0], hi[1], hi[2], hi[3]);
             st_shared_v4(lo_addr, lo[0], lo[1], lo[2], lo[3]);
         };
+        int st_s = 0;
+        uint32_t st_ph = 0;
         auto store = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool okx) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1;
+            const int s = st_s;
+            const uint32_t ph = st_ph;
+            if (++st_s == S) { st_s = 0; st_ph ^= 1; }
             if (PRE != 0) {
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)

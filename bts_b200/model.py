@@ -75,6 +75,45 @@ class Conv2dTC(nn.Conv2d):
         return torch.sigmoid(self.forward(x))
 
 
+def fuse_enabled(x):
+    """the fused glue path (bts_b200/glue.py) is taken for fp32 CUDA tensors when the tensor-core backend is active"""
+    from . import fused, glue
+    return fused.FUSE and conv_backend() == "tc" and glue.eligible(x)
+
+
+class BatchNormTC(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters / buffers / state_dict) whose forward + backward run on our streaming kernels;
+    `_fuse_relu` folds the ReLU module that follows it in torchvision's `features` (norm0 -> relu0)."""
+    _fuse_relu = False
+
+    def forward(self, x):
+        if fuse_enabled(x) and self.affine:
+            from . import glue
+            return glue.bn_act(x, self, relu=self._fuse_relu)
+        y = super().forward(x)
+        return F.relu(y) if self._fuse_relu else y
+
+
+class ReluFolded(nn.Identity):
+    """stands where torchvision's `relu0` was: the ReLU already ran inside the preceding BatchNormTC"""
+
+
+def _transition_class():
+    from torchvision.models.densenet import _Transition
+
+    class TransitionTC(_Transition):
+        """torchvision DenseNet transition [BN -> ReLU -> 1x1 conv -> 2x2 avg-pool]: BN + ReLU folded into the conv's
+        A-operand prologue, pooling on our streaming kernel"""
+
+        def forward(self, x):
+            if fuse_enabled(x) and self.norm.affine and self.conv.bias is None:
+                from . import glue
+                return glue.avgpool2(glue.bn_relu_conv(x, self.norm, self.conv.weight))
+            return super().forward(x)
+
+    return _Transition, TransitionTC
+
+
 def _dense_block_class():
     from torchvision.models.densenet import _DenseBlock
 
@@ -95,11 +134,22 @@ def adopt_convs(module):
     """Re-class every eligible nn.Conv2d (-> Conv2dTC) and DenseNet block (-> fused DenseBlockTC) of a torchvision
     module tree in place -- parameter names, shapes and init are untouched."""
     base, fusedcls = _dense_block_class()
+    tbase, tcls = _transition_class()
     for m in module.modules():
         if type(m) is nn.Conv2d:
             m.__class__ = Conv2dTC
         elif type(m) is base:
             m.__class__ = fusedcls
+        elif type(m) is tbase:
+            m.__class__ = tcls
+    # DenseNet `features`: norm0 (+ relu0 folded) and norm5 on the streaming BatchNorm kernels
+    if isinstance(module, nn.Sequential) and hasattr(module, "norm0") and type(module.norm0) is nn.BatchNorm2d:
+        module.norm0.__class__ = BatchNormTC
+        if isinstance(getattr(module, "relu0", None), nn.ReLU):
+            module.norm0._fuse_relu = True
+            module.relu0 = ReluFolded()
+    if isinstance(module, nn.Sequential) and hasattr(module, "norm5") and type(module.norm5) is nn.BatchNorm2d:
+        module.norm5.__class__ = BatchNormTC
     return module
 
 
@@ -126,6 +176,14 @@ class atrous_conv(nn.Sequential):
         self.atrous_conv = body
 
     def forward(self, x):
+        if fuse_enabled(x):
+            from . import glue
+            seq = self.atrous_conv.aconv_sequence
+            if hasattr(self.atrous_conv, "first_bn"):
+                b = glue.bn_relu_conv(x, self.atrous_conv.first_bn, seq[1].weight)
+            else:
+                b = glue.conv_act(x, seq[1].weight, pre_relu=True)
+            return glue.bn_relu_conv(b, seq[2], seq[4].weight, seq[4].padding[0], seq[4].dilation[0])
         return self.atrous_conv(x)
 
 
@@ -138,7 +196,12 @@ class upconv(nn.Module):
         self.conv = _conv(in_channels, out_channels, 3)
         self.ratio = ratio
 
-    def forward(self, x):
+    def forward(self, x, pre_relu=False):
+        if fuse_enabled(x) and self.ratio == 2:
+            from . import glue                   # up-sample folded into the im2col map, ELU in the epilogue
+            return glue.conv_act(x, self.conv.weight, 1, 1, pre_relu=pre_relu, up=True, act="elu")
+        if pre_relu:
+            x = F.relu(x)
         return self.elu(self.conv(F.interpolate(x, scale_factor=self.ratio, mode="nearest")))
 
 
@@ -165,11 +228,20 @@ class reduction_1x1(nn.Sequential):
             cin, cout = cout, cout // 2
 
     def trunk(self, net):
-        if self.is_final:                       # last stage = Sequential(1x1 conv, Sigmoid): fused single-channel head
-            for name, m in self.reduc.named_children():
-                net = m[0].forward_sigmoid(net) if name == "final" else m(net)
-            return net
-        return self.reduc(net)
+        fuse = fuse_enabled(net)
+        glue = None
+        if fuse:
+            from . import glue
+        for name, m in self.reduc.named_children():
+            if name == "final":                 # Sequential(1x1 conv 8->1, Sigmoid): fused single-channel head kernel
+                net = m[0].forward_sigmoid(net)
+            elif name == "plane_params":
+                net = m(net)
+            elif fuse:                          # Sequential(1x1 conv, ELU): ELU in the conv epilogue
+                net = glue.conv_act(net, m[0].weight, 0, 1, act="elu")
+            else:
+                net = m(net)
+        return net
 
     def forward(self, net):
         net = self.trunk(net)
@@ -246,9 +318,48 @@ class bts(nn.Module):
         self.get_depth = nn.Sequential(_conv(nf // 16, 1, 3), nn.Sigmoid())
 
     def forward(self, features, focal):
+        if fuse_enabled(features[4]):
+            return self._forward_fused(features, focal)
+        return self._forward_eager(features, focal)
+
+    def _forward_fused(self, features, focal):
+        """bts.forward (reference pytorch/bts.py:196-266) over the fused units of bts_b200/glue.py: no ATen BatchNorm /
+        ReLU / ELU / interpolate / cat kernels; every conv (fwd, dgrad, wgrad) on the tcgen05 engine."""
+        from . import glue as G
         skip0, skip1, skip2, skip3 = features[0], features[1], features[2], features[3]
         md = self.params.max_depth
-        x = self.bn5(self.upconv5(F.relu(features[4])))                                   # H/16
+        c3 = lambda seq: seq[0].weight          # Sequential(3x3 conv, ELU)
+        x = G.bn_act(self.upconv5(features[4], pre_relu=True), self.bn5)                  # H/16
+        x = G.conv_act(G.cat_nhwc([x, skip3]), c3(self.conv5), 1, 1, act="elu")
+        cat4 = G.cat_nhwc([G.bn_act(self.upconv4(x), self.bn4), skip2])                   # H/8
+        iconv4 = G.bn_act(G.conv_act(cat4, c3(self.conv4), 1, 1, act="elu"), self.bn4_2)
+        d3 = self.daspp_3(iconv4)
+        d6 = self.daspp_6(G.cat_nhwc([cat4, d3]))
+        d12 = self.daspp_12(G.cat_nhwc([cat4, d3, d6]))
+        d18 = self.daspp_18(G.cat_nhwc([cat4, d3, d6, d12]))
+        d24 = self.daspp_24(G.cat_nhwc([cat4, d3, d6, d12, d18]))
+        feat8 = G.conv_act(G.cat_nhwc([iconv4, d3, d6, d12, d18, d24]), c3(self.daspp_conv), 1, 1, act="elu")
+
+        depth_8x8_scaled, d8_ds = ops.plane_head_lpg(self.reduc8x8.trunk(feat8), 8, md, ds_stride=4)
+        x = G.bn_act(self.upconv3(feat8), self.bn3)                                       # H/4
+        iconv3 = G.conv_act(G.cat_nhwc([x, skip1, d8_ds]), c3(self.conv3), 1, 1, act="elu")
+        depth_4x4_scaled, d4_ds = ops.plane_head_lpg(self.reduc4x4.trunk(iconv3), 4, md, ds_stride=2)
+        x = G.bn_act(self.upconv2(iconv3), self.bn2)                                      # H/2
+        iconv2 = G.conv_act(G.cat_nhwc([x, skip0, d4_ds]), c3(self.conv2), 1, 1, act="elu")
+        depth_2x2_scaled = ops.plane_head_lpg(self.reduc2x2.trunk(iconv2), 2, md)
+        up1 = self.upconv1(iconv2)                                                        # H
+        reduc1x1 = self.reduc1x1(up1)
+        iconv1 = G.conv_act(G.cat_nhwc([up1, reduc1x1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled]),
+                            c3(self.conv1), 1, 1, act="elu")
+        final_depth = md * self.get_depth[0].forward_sigmoid(iconv1)      # Sequential(3x3 conv 32->1, Sigmoid), fused
+        if self.params.dataset == "kitti":
+            final_depth = final_depth * focal.view(-1, 1, 1, 1).float() / 715.0873
+        return depth_8x8_scaled, depth_4x4_scaled, depth_2x2_scaled, reduc1x1, final_depth
+
+    def _forward_eager(self, features, focal):
+        skip0, skip1, skip2, skip3 = features[0], features[1], features[2], features[3]
+        md = self.params.max_depth
+        x = self.bn5(self.upconv5(features[4], pre_relu=True))                                   # H/16
         x = self.conv5(torch.cat([x, skip3], 1))
         cat4 = torch.cat([self.bn4(self.upconv4(x)), skip2], 1)                           # H/8
         iconv4 = self.bn4_2(self.conv4(cat4))

@@ -159,6 +159,40 @@ int bts_bn_relu_bwd_apply(const float *x, long long x_pixel_stride, const float 
                           long long M, int C, const float *scale, const float *shift, const float *coef, float *out,
                           long long out_pixel_stride, int accumulate, void *stream);
 
+/* generalised forms with an explicit `relu` flag (relu=0: plain BatchNorm, as the decoder's bn5/bn4/bn4_2/bn3/bn2 which
+ * feed a concat, bts.py:200-246); the *_relu_* entry points above are these with relu=1. */
+int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride, long long M,
+                      int C, const float *scale, const float *shift, const float *mean, const float *invstd, int relu,
+                      double *S1, double *S2, float *coef, void *stream);
+int bts_bn_bwd_apply(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride, long long M,
+                     int C, const float *scale, const float *shift, const float *coef, int relu, float *out,
+                     long long out_pixel_stride, int accumulate, void *stream);
+
+/* ---- streaming NHWC glue kernels of the decoder / encoder transitions (csrc/elem.cu) ---------------------------
+ * All take explicit pixel strides (floats) so channel slices of wider slabs are read / written in place.
+ *   bts_bn_apply       out = x*scale + shift [, ReLU]   -- BatchNorm2d forward given (scale, shift) from bts_bn_finalize /
+ *                      bts_bn_fold (decoder BNs bts.py:154-182; torchvision norm0 / norm5)
+ *   bts_elu_bwd        out = gy * (y > 0 ? 1 : y + 1)   -- backward of nn.ELU() through its saved OUTPUT y (bts.py:72,79,...)
+ *   bts_upsample2_sum  out[b,y,x,:] = sum of g[b,2y..2y+1,2x..2x+1,:]  -- backward of F.interpolate(scale_factor=2,
+ *                      mode='nearest') (bts.py:77); relu_src != NULL additionally gates by relu_src > 0 (torch.nn.ReLU in
+ *                      front of upconv5, bts.py:198)
+ *   bts_copy_channels  dst (=|+=) src over M pixels x C channels -- torch.cat along channels / its backward (bts.py:201-260)
+ *   bts_zero_channels  dst[:, c0:c1] = 0                -- alignment padding channels of concat3 (225) / concat2 (161)
+ *   bts_avgpool2_fwd/bwd  2x2 stride-2 average pooling of the DenseNet transitions (torchvision densenet.py `pool`) */
+int bts_bn_apply(const float *x, long long x_pixel_stride, long long M, int C, const float *scale, const float *shift,
+                 int relu, float *out, long long out_pixel_stride, void *stream);
+int bts_elu_bwd(const float *gy, long long gy_pixel_stride, const float *y, long long y_pixel_stride, long long M, int C,
+                float *out, long long out_pixel_stride, void *stream);
+int bts_upsample2_sum(const float *g, long long g_pixel_stride, int B, int H, int W, int C, const float *relu_src,
+                      long long relu_pixel_stride, float *out, long long out_pixel_stride, void *stream);
+int bts_copy_channels(const float *src, long long src_pixel_stride, long long M, int C, float *dst,
+                      long long dst_pixel_stride, int accumulate, void *stream);
+int bts_zero_channels(float *dst, long long dst_pixel_stride, long long M, int c0, int c1, void *stream);
+int bts_avgpool2_fwd(const float *x, long long x_pixel_stride, int B, int Hout, int Wout, int C, float *out,
+                     long long out_pixel_stride, void *stream);
+int bts_avgpool2_bwd(const float *g, long long g_pixel_stride, int B, int Hout, int Wout, int C, float *gx,
+                     long long gx_pixel_stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
