@@ -21,7 +21,8 @@ constexpr int CHUNK = KP * 128;              // one 32-channel chunk of a k-bloc
 constexpr int A_BYTES = 4 * CHUNK;           // 8 KB (hi or lo)
 constexpr int MAX_TAPS = 9;
 constexpr int MAX_STAGES = 4;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 576;               // 2 control warps + 16 producer warps (4 quarters of 128 threads)
+constexpr int PRODUCERS = 512;
 constexpr int SMEM_BUDGET = 224 * 1024;
 
 struct W2Params {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(full(s), 256);
+            mbar_init(full(s), PRODUCERS);
             mbar_init(empty(s), 1);
         }
         mbar_init(accum_full, 1);
@@ -125,27 +126,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             umma_commit(accum_full);
         }
     } else if (warp >= 2) {
-        const int pt = threadIdx.x - 64;           // 0..255
+        // 16 producer warps (round 1 ran 8: ncu showed ~9 cycles between a warp's instructions and 2.5 warps per
+        // scheduler -- the per-thread instruction stream, not the tensor pipe, set the k-block time).  Quarter q of the
+        // producers owns the x chunk q and the dY taps t == q (mod 4): at most 1 + 6 sixteen-byte units per thread.
+        const int pt = threadIdx.x - 64;           // 0..511
         const int unit = pt & 7;                   // 16-byte unit of the 128-byte row
         const int row = (pt >> 3) & 15;            // pixel row of the 16-pixel k-block
-        const int half = pt >> 7;                  // A: chunks {2*half, 2*half+1};  dY: taps t == half (mod 2)
+        const int half = pt >> 7;                  // quarter 0..3: A chunk `half`;  dY: taps t == half (mod 4)
         constexpr bool AFF = PRE >= 2;
         constexpr bool RELU = (PRE & 1) != 0;
         const uint32_t roff = mn_swizzle_off(row, unit);
         const int xs = (int)p.xs, dys = (int)p.dys;
-        const int cbx = ci_tile * BLOCK_CI + half * 64 + unit * 4;    // first x channel of this thread (chunk 2*half)
+        const int cbx = ci_tile * BLOCK_CI + half * 32 + unit * 4;    // first x channel of this thread (chunk `half`)
         const int cbd = co0 + unit * 4;                               // first dY channel (chunk 0)
         const float *__restrict__ xg = p.x;
         const float *__restrict__ dg = p.dy;
-        float sc[2][4], sh[2][4];
+        float sc[1][4], sh[1][4];
         if (AFF) {
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    sc[ch][e] = s_scale[half * 64 + ch * 32 + unit * 4 + e];
-                    sh[ch][e] = s_shift[half * 64 + ch * 32 + unit * 4 + e];
-                }
+            for (int e = 0; e < 4; ++e) {
+                sc[0][e] = s_scale[half * 32 + unit * 4 + e];
+                sh[0][e] = s_shift[half * 32 + unit * 4 + e];
+            }
         }
         // input-pixel coordinates of this thread's row, advanced by 16 pixels per k-block (no divisions in the loop)
         int qx, qy, qb;
@@ -156,24 +158,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             qy = r % p.Hin;
             qb = r / p.Hin;
         }
-        constexpr int NBU = 10;                    // dY units per thread per k-block: <= 5 taps x 2 chunks
-        // tap offsets of this thread's taps (t = half, half+2, ...), computed once: no divisions in the k-loop
+        constexpr int NBU = 6;                     // dY units per thread per k-block: <= 3 taps x 2 chunks
+        constexpr int NAU = 1;                     // x units per thread per k-block
+        // tap offsets of this thread's taps (t = half, half+4, half+8), computed once: no divisions in the k-loop
         int toy[NBU / 2], tox[NBU / 2];
 #pragma unroll
         for (int j = 0; j < NBU / 2; ++j) {
-            const int t = half + 2 * j;
+            const int t = half + 4 * j;
             const int ky = t / p.KW, kx = t - ky * p.KW;
             toy[j] = ky * p.dil - p.pad;
             tox[j] = kx * p.dil - p.pad;
         }
-        auto load = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool &okx) {
+        auto load = [&](int it, F4(&va)[NAU], F4(&vb)[NBU], bool &okx) {
             const int q = (kb0 + it) * KP + row;
             okx = q < p.Mq;
             // ---- x~ tile: this thread's pixel, channels of its two chunks
             const int sy = UP ? (qy >> 1) : qy, sx = UP ? (qx >> 1) : qx;
             const int xoff = ((qb * p.Hs + sy) * p.Ws + sx) * xs;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NAU; ++ch) {
                 const int c = cbx + ch * 32;
                 const bool live = okx && c < p.Cin;
                 if (VEC) {
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             // ---- shifted dY tiles: taps t = half, half+2, ...; output pixel (qy - dy_t, qx - dx_t)
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
-                const int t = half + 2 * j;
+                const int t = half + 4 * j;
                 const int py = qy - toy[j], px = qx - tox[j];
                 const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
                 const int doff = ((qb * p.Hout + py) * p.Wout + px) * dys;
@@ -245,13 +248,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         };
         int st_s = 0;
         uint32_t st_ph = 0;
-        auto store = [&](int it, F4(&va)[2], F4(&vb)[NBU], bool okx) {
+        auto store = [&](int it, F4(&va)[NAU], F4(&vb)[NBU], bool okx) {
             const int s = st_s;
             const uint32_t ph = st_ph;
             if (++st_s == S) { st_s = 0; st_ph ^= 1; }
             if (PRE != 0) {
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
+                for (int ch = 0; ch < NAU; ++ch)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float a = va[ch].v[e];
@@ -269,13 +272,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             const uint32_t a_hi = base + (uint32_t)s * (uint32_t)p.stage_bytes, a_lo = a_hi + A_BYTES;
             const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_half;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const uint32_t o = (uint32_t)(half * 2 + ch) * CHUNK + roff;
+            for (int ch = 0; ch < NAU; ++ch) {
+                const uint32_t o = (uint32_t)(half + ch) * CHUNK + roff;
                 split_store(a_hi + o, a_lo + o, va[ch]);
             }
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
-                const int t = half + 2 * j;
+                const int t = half + 4 * j;
                 if (t < taps) {
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch)
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             mbar_arrive(full(s));
         };
         {
-            F4 a0[2], a1[2], b0[NBU], b1[NBU];
+            F4 a0[NAU], a1[NAU], b0[NBU], b1[NBU];
             bool k0 = false, k1 = false;
             int it = 0;
             if (it < nkb) load(it, a0, b0, k0);
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         const int q4 = warp & 3;
         const int ci = ci_tile * BLOCK_CI + q4 * 32 + lane;
         const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0) && ((co0 & 3) == 0);
-        for (int t = half; t < taps; t += 2) {
+        for (int t = half; t < taps; t += 4) {
             float *prow = p.part + (((long long)split * taps + t) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + co0;
             for (int cc = 0; cc < ncol; cc += 8) {
                 uint32_t r[8];

@@ -20,7 +20,8 @@ constexpr int MAX_N = 128;
 constexpr int STAGES = 3;
 constexpr int CHUNK_BYTES = BLOCK_KP * 128;  // one 32-channel chunk of a k-block: 4 KB
 constexpr int A_BYTES = 4 * CHUNK_BYTES;     // 16 KB (hi or lo)
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 576;               // 2 control warps + 2 producer groups x 8 warps
+constexpr int GROUP_THREADS = 256;
 
 struct WgradParams {
     const float *x; long long xs;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full(s), 256);      // both producer groups (x tile + dY tile) arrive
+            mbar_init(full(s), 2 * GROUP_THREADS);      // both producer groups (x tile + dY tile) arrive
             mbar_init(empty(s), 1);
         }
         mbar_init(accum_full, 1);
@@ -120,23 +121,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             umma_commit(accum_full);
         }
     } else if (warp >= 2) {
+        // 8 warps per group (round 1 ran 4 with two pixel rows per thread: ~9 cycles between a warp's instructions at
+        // 2.5 warps per scheduler made the producers, not the tensor pipe, set the k-block time): one pixel row of the
+        // 32-pixel k-block per thread, 4 sixteen-byte units (one per 32-channel chunk).
         const int pt = threadIdx.x - 64;
-        const int grp = pt >> 7;                   // group 0 produces the x (A) tiles, group 1 the dY (B) tiles
-        const int t = pt & 127;
+        const int grp = pt >> 8;                   // group 0 produces the x (A) tiles, group 1 the dY (B) tiles
+        const int t = pt & 255;
         const int unit = t & 7;                    // 16-byte unit of the 128-byte row
-        const int r0 = t >> 3;                     // pixel rows r0, r0 + 16 of the 32-pixel k-block
+        const int r0 = t >> 3;                     // pixel row r0 of the 32-pixel k-block
         constexpr bool AFF = PRE >= 2;
         constexpr bool RELU = (PRE & 1) != 0;
-        uint32_t roff[8];
+        constexpr int NU = 4;                      // units per thread per k-block
+        uint32_t roff[NU];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) roff[i] = (uint32_t)(i >> 1) * CHUNK_BYTES + mn_swizzle_off(r0 + 16 * (i & 1), unit);
+        for (int i = 0; i < NU; ++i) roff[i] = (uint32_t)i * CHUNK_BYTES + mn_swizzle_off(r0, unit);
 
         // hi/lo split + swizzled stores of up to 8 units (4 chunks x 2 rows); only `nlive` chunks are written
         // (the A regions were zeroed once, so dead channel chunks stay zero)
-        auto split_store = [&](uint32_t t_hi, uint32_t t_lo, F4(&v)[8], int nlive) {
+        auto split_store = [&](uint32_t t_hi, uint32_t t_lo, F4(&v)[NU], int nlive) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if ((i >> 1) < nlive) {
+            for (int i = 0; i < NU; ++i) {
+                if (i < nlive) {
                     float hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -171,22 +176,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             }
             const float *__restrict__ xg = p.x;
             // output-pixel coordinates of this thread's two rows, advanced by 32 pixels per k-block (no divisions)
-            int px[2], py[2], pb[2];
+            int px[1], py[1], pb[1];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int m = kb0 * BLOCK_KP + r0 + 16 * h;
+            for (int h = 0; h < 1; ++h) {
+                const int m = kb0 * BLOCK_KP + r0;
                 px[h] = m % p.Wout;
                 const int q = m / p.Wout;
                 py[h] = q % p.Hout;
                 pb[h] = q / p.Hout;
             }
-            auto load_x = [&](int it, F4(&v)[8], uint32_t &mask) {
+            auto load_x = [&](int it, F4(&v)[NU], uint32_t &mask) {
                 const int kb = kb0 + it;
-                int off[2];
-                bool ok[2];
+                int off[1];
+                bool ok[1];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int m = kb * BLOCK_KP + r0 + 16 * h;
+                for (int h = 0; h < 1; ++h) {
+                    const int m = kb * BLOCK_KP + r0;
                     const int yy = py[h] * p.stride + dyo, xx = px[h] * p.stride + dxo;
                     ok[h] = m < p.M && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
                     const int sy = UP ? (yy >> 1) : yy, sx = UP ? (xx >> 1) : xx;
@@ -197,10 +202,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                         if (++py[h] == p.Hout) { py[h] = 0; ++pb[h]; }
                     }
                 }
-                mask = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+                mask = ok[0] ? 1u : 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int h = i & 1, chunk = i >> 1;
+                for (int i = 0; i < NU; ++i) {
+                    const int h = 0, chunk = i;
                     const int c = cb + chunk * 32;
                     const bool live = chunk < nlive && ok[h] && c < p.Cin;
                     if (VEC) {
@@ -222,19 +227,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     }
                 }
             };
-            auto store_x = [&](int it, F4(&v)[8], uint32_t mask) {
+            auto store_x = [&](int it, F4(&v)[NU], uint32_t mask) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 if (PRE != 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < NU; ++i)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             float a = v[i].v[e];
                             if (AFF) {
-                                a = fmaf(a, sc[i >> 1][e], sh[i >> 1][e]);
+                                a = fmaf(a, sc[i][e], sh[i][e]);
                                 if (RELU) a = fmaxf(a, 0.f);
-                                a = ((mask >> (i & 1)) & 1u) ? a : 0.f;
+                                a = (mask & 1u) ? a : 0.f;
                             } else {
                                 a = fmaxf(a, 0.f);
                             }
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                 fence_proxy_async();
                 mbar_arrive(full(s));
             };
-            F4 va[8], vb[8];
+            F4 va[NU], vb[NU];
             uint32_t ma = 0, mb = 0;
             int it = 0;
             if (it < nkb) load_x(it, va, ma);
@@ -266,12 +271,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             const int nchunk = (n_tile + 31) >> 5;
             const int cb = nt * n_tile + unit * 4;
             const float *__restrict__ dg = p.dy;
-            auto load_d = [&](int it, F4(&v)[8]) {
+            auto load_d = [&](int it, F4(&v)[NU]) {
                 const int kb = kb0 + it;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int h = i & 1, chunk = i >> 1;
-                    const int m = kb * BLOCK_KP + r0 + 16 * h;
+                for (int i = 0; i < NU; ++i) {
+                    const int chunk = i;
+                    const int m = kb * BLOCK_KP + r0;
                     const int c = cb + chunk * 32;
                     const bool live = chunk < nchunk && m < p.M && c < p.Cout;
                     if (VEC) {
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     }
                 }
             };
-            auto store_d = [&](int it, F4(&v)[8]) {
+            auto store_d = [&](int it, F4(&v)[NU]) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty(s), ph ^ 1);
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                 fence_proxy_async();
                 mbar_arrive(full(s));
             };
-            F4 va[8], vb[8];
+            F4 va[NU], vb[NU];
             int it = 0;
             if (it < nkb) load_d(it, va);
             for (; it < nkb; it += 2) {
@@ -316,7 +321,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             }
         }
 
-        // ---- epilogue: TMEM lane = input channel, columns = output channels
+        // ---- epilogue: TMEM lane = input channel, columns = output channels (first 4 warps of each group: one per
+        //      TMEM lane quarter; group 0 takes the low half of the columns, group 1 the high half)
+        if (t < 128) {
         mbar_wait(accum_full, 0);
         tc_fence_after();
         const int q = warp & 3;
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     }
                 }
             }
+        }
         }
     }
     tc_fence_before();

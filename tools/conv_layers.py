@@ -44,6 +44,7 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+tc_only = len(sys.argv) > 2 and sys.argv[2] == "tc"      # skip the cuDNN column (A/B sweeps of the engine)
 tot_tc = tot_cd = 0.0
 print("%-26s %9s %9s %9s %9s" % ("layer", "tc ms", "tc TF/s", "cudnn ms", "cudnn TF/s"))
 for name, Cin, H, W, Cout, k, dil, up in LAYERS:
@@ -69,7 +70,7 @@ for name, Cin, H, W, Cout, k, dil, up in LAYERS:
         xu = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
         f_cd = lambda: torch.ops.aten.convolution_backward(gy, xu, w, None, [1, 1], [pad, pad], [dil, dil], False, [0, 0], 1, [False, True, False])
     t_tc = timeit(f_tc)
-    t_cd = timeit(f_cd)
+    t_cd = float("nan") if tc_only else timeit(f_cd)
     tot_tc += t_tc; tot_cd += t_cd
     print("%-26s %9.3f %9.1f %9.3f %9.1f" % (name, t_tc, flops / t_tc / 1e9, t_cd, flops / t_cd / 1e9))
 print("total %.2f ms (tc) vs %.2f ms (cudnn)" % (tot_tc, tot_cd))
