@@ -98,8 +98,11 @@ SIGNATURES = {
     "bts_zero_channels": [_p, _ll, _ll, _i, _i, _p],
     "bts_avgpool2_fwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
     "bts_avgpool2_bwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
+    "bts_conv_pw_wgrad_eligible": [_i, _i],
+    "bts_conv_pw_wgrad_workspace_floats": [_i, _i],
+    "bts_conv_pw_wgrad": [_p, _ll, _p, _ll, _ll, _i, _i, _p, _p, _ll, _ll, _p],
 }
-RESTYPES = {"bts_conv_packed_floats": ctypes.c_longlong}
+RESTYPES = {"bts_conv_packed_floats": ctypes.c_longlong, "bts_conv_pw_wgrad_workspace_floats": ctypes.c_longlong}
 
 
 def lib():

@@ -17,6 +17,8 @@ ACT = {None: 0, "none": 0, "elu": 1, "sigmoid": 2}
 import os as _os
 WGRAD_BACKEND = _os.environ.get("BTS_B200_WGRAD", "tc")     # tc: tcgen05 wgrad kernel | aten: library scaffold
 
+PW_WGRAD = _os.environ.get("BTS_B200_PW_WGRAD", "1") == "1"   # CUDA-core wgrad for narrow 1x1 layers (csrc/pointwise.cu)
+PW_MIN_PIXELS = 200000                                        # below this the tensor-core path is already short
 TRACE = _os.environ.get("BTS_B200_TRACE", "0") == "1"     # per-call CUDA-event timing, aggregated by shape
 trace_log = []
 
@@ -138,6 +140,18 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
     B, Cin, Hs, Ws = x.shape
     Cout, _, KH, KW = weight_shape
     L = _lib.lib()
+    if (PW_WGRAD and KH == 1 and KW == 1 and stride == 1 and padding == 0 and pre_scale is None and not pre_relu
+            and not upsample2 and precision == 0 and B * Hs * Ws >= PW_MIN_PIXELS and L.bts_conv_pw_wgrad_eligible(Cin, Cout)):
+        # narrow 1x1 layers of the reduction heads: HBM-bound CUDA-core kernel (csrc/pointwise.cu)
+        ws = torch.empty(L.bts_conv_pw_wgrad_workspace_floats(Cin, Cout), device=x.device, dtype=torch.float32)
+        gw = torch.empty_strided(tuple(weight_shape), tuple(weight_strides), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            rc = _traced("pwwgrad", "%dx%dx%d %d->%d k1" % (B, Hs, Ws, Cin, Cout),
+                         lambda: L.bts_conv_pw_wgrad(_ptr(x), xs, _ptr(gy), gs, B * Hs * Ws, Cin, Cout, _ptr(ws), _ptr(gw),
+                                                     weight_strides[0], weight_strides[1], _stream()))
+        _lib.check(rc, "bts_conv_pw_wgrad")
+        _lib.count(2)
+        return gw
     split = ctypes.c_int(0)
     wsf = ctypes.c_longlong(0)
     _lib.check(L.bts_conv_wgrad_plan(B, gy.shape[2], gy.shape[3], Cin, Cout, KH, KW, ctypes.byref(split), ctypes.byref(wsf)),

@@ -39,13 +39,14 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // fp32 elements per k-block = one 128-byte row
-constexpr int MAX_N = 128;
+constexpr int MAX_N = 256;                  // one tcgen05.mma covers up to 256 output channels
 constexpr int A_TILE_BYTES = BLOCK_M * 128; // 16 KB (hi or lo)
 constexpr int NUM_THREADS = 448;
 constexpr int PRODUCER_THREADS = 128;       // per group
 constexpr int MAX_CIN_SMEM = 4096;          // pre-op scale/shift staged in smem (32 KB at most)
 constexpr int EPI_THREADS = 128;
-constexpr int TMEM_COLS = 256;              // two 128-column fp32 accumulators
+constexpr int TMEM_COLS = 512;              // two 256-column fp32 accumulators (all of TMEM)
+constexpr int ACC_COLS = 256;
 
 struct ConvParams {
     const float *x;          // NHWC source, pixel stride xs floats
@@ -70,7 +71,6 @@ struct ConvParams {
     int KC;                  // ceil(Cin/32)
     int KB;                  // KH*KW*KC k-blocks
     int stages, stage_bytes; // smem ring: as many (A hi/lo + B hi/lo) stages as fit
-    int sa, sb, ring;        // async variant: A (hi/lo) stages, weight slots, raw landing slots (even)
     tc::FastDiv fd_wout, fd_hout, fd_ntiles;
 };
 
@@ -215,12 +215,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+            // Instruction-count economy (measured, round 1): a tcgen05.mma with M=128, K=8 (tf32) costs ~115-130 cycles
+            // whatever N is -- fetching the 128 A rows from shared memory sets the pace -- so every layer ran at ~1400
+            // cycles per k-block (12 MMAs) regardless of Cout, load latency or producer instruction count.  Hence:
+            //   * n_tile <= 128: B_hi and B_lo are adjacent in the stage, so ONE instruction with N = 2*n_tile computes
+            //     A_hi*[B_hi;B_lo] into 2*n_tile accumulator columns (the epilogue adds the two halves); the third
+            //     product A_lo*B_hi is a second instruction: 2 MMAs per k-step instead of 3;
+            //   * n_tile <= 256 is one tile (3 MMAs per k-step, the activation tile produced once) instead of two tiles.
+            const bool stack = n_tile <= 128;
             const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
+            const uint32_t idesc2 = make_idesc(BLOCK_M, 2 * n_tile);
             int s = 0;
             uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                 mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb) {
@@ -233,13 +242,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     const uint32_t b_lo = b_hi + n_tile * 128;
                     const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
                     if (p.precision == 0) {
+                        if (stack) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
-                            umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < BLOCK_K / 8; ++k) {
+                                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc2, (kb | k) != 0);   // A_hi * [B_hi ; B_lo]
+                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);                // A_lo * B_hi
+                            }
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+                            for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
+                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                        }
                     } else {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / 8; ++k)
@@ -421,12 +438,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
             mbar_wait_sleep(tmem_full(acc), (uint32_t)((ti >> 1) & 1));
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            const bool stack = n_tile <= 128 && p.precision == 0;   // columns [n_tile, 2 n_tile) hold A_hi * B_lo
             for (int cc = 0; cc < n_tile; cc += 16) {
                 uint32_t r[16];
                 tmem_ld8(t_addr + (uint32_t)cc, reinterpret_cast<uint32_t(&)[8]>(r[0]));
                 tmem_ld8(t_addr + (uint32_t)cc + 8, reinterpret_cast<uint32_t(&)[8]>(r[8]));
-                tmem_ld_wait();
+                if (stack) {
+                    uint32_t r2[16];
+                    tmem_ld8(t_addr + (uint32_t)(n_tile + cc), reinterpret_cast<uint32_t(&)[8]>(r2[0]));
+                    tmem_ld8(t_addr + (uint32_t)(n_tile + cc) + 8, reinterpret_cast<uint32_t(&)[8]>(r2[8]));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+                } else {
+                    tmem_ld_wait();
+                }
                 if (m < p.M) {
                     const int cbase = nt * n_tile + cc;          // absolute output channel
 #pragma unroll
@@ -459,350 +486,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 }
 
 
-// ------------------------------------------------------------------------------------------- async-producer variant
-// ncu + the per-layer sweep of round 1 showed one number for every layer regardless of N: ~1400 cycles per k-block.
-// The producers' 128-bit loads miss L1 and (13 %) L2, a warp-wide instruction gathers 4 pixel rows, so practically
-// every k-block waits for an HBM round trip, and the register ping-pong above keeps only ONE k-block per group in
-// flight.  Here the global loads are cp.async (LDGSTS) copies into a raw landing ring in shared memory: no registers are
-// held, so each group keeps ring/2 k-blocks (default 3 = 48 KB) in flight.  Every thread reads back exactly the 8
-// chunks it copied itself (cp.async.wait_group is all the synchronisation that needs), converts (pre-op, hi/lo split)
-// and writes the swizzled operand stage as before.  The weight tiles get their own ring (sb slots) so that neither
-// operand's latency is tied to the number of A stages.
-//   smem: [sa x (A_hi 16K | A_lo 16K)] [sb x (B_hi | B_lo)] [ring x 16K raw] [pre scale/shift] [mbarriers]
-constexpr int MAX_SA = 4, MAX_SB = 6, MAX_RING = 8;
-constexpr int RAW_BYTES = BLOCK_M * 128;    // one k-block of raw fp32 activations
-
-template <int PRE, bool UP>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_async_kernel(const ConvParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
-    const int SA = p.sa, SB = p.sb, R = p.ring;
-    const int n_tile = p.n_tile;
-    const uint32_t b_slot = 2u * (uint32_t)n_tile * 128u;
-    const uint32_t a_base = base;
-    const uint32_t b_base = a_base + (uint32_t)SA * 2u * A_TILE_BYTES;
-    const uint32_t r_base = b_base + (uint32_t)SB * b_slot;
-    const uint32_t pre_off = (r_base - base) + (uint32_t)R * RAW_BYTES;
-    float *s_scale = reinterpret_cast<float *>(sm + pre_off);
-    float *s_shift = s_scale + p.KC * 32;
-    const uint32_t bar_off = pre_off + (PRE >= 2 ? (uint32_t)p.KC * 32u * 8u : 0u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + bar_off);
-    const uint32_t bar0 = base + bar_off;
-    auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto empty_a = [&](int s) { return bar0 + 8u * (MAX_SA + s); };
-    auto full_b = [&](int s) { return bar0 + 8u * (2 * MAX_SA + s); };
-    auto empty_b = [&](int s) { return bar0 + 8u * (2 * MAX_SA + MAX_SB + s); };
-    auto tmem_full = [&](int a) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + a); };
-    auto tmem_empty = [&](int a) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 2 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_SA + 2 * MAX_SB + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KB = p.KB;
-    const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_kb = my_tiles * KB;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; ++s) {
-            mbar_init(full_a(s), PRODUCER_THREADS);
-            mbar_init(empty_a(s), 1);
-        }
-        for (int s = 0; s < SB; ++s) {
-            mbar_init(full_b(s), 1);
-            mbar_init(empty_b(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), EPI_THREADS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    if (PRE >= 2) {
-        for (int c = threadIdx.x; c < p.KC * 32; c += NUM_THREADS) {
-            s_scale[c] = c < p.Cin ? p.pre_scale[c] : 0.f;
-            s_shift[c] = c < p.Cin ? p.pre_shift[c] : 0.f;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== weight loader: its own ring of sb slots =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int nt = tile - (int)fdiv((uint32_t)tile, p.fd_ntiles) * p.n_tiles;
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * b_slot;
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait_sleep(empty_b(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full_b(s), b_slot);
-                    bulk_copy_g2s(b_base + (uint32_t)s * b_slot, src + (size_t)kb * b_slot, b_slot, full_b(s));
-                    if (++s == SB) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
-            int sa = 0, sb = 0;
-            uint32_t pha = 0, phb = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int acc = ti & 1;
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
-                mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);
-                tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(full_b(sb), phb);
-                    mbar_wait(full_a(sa), pha);
-                    tc_fence_after();
-                    const uint32_t a_hi = a_base + (uint32_t)sa * 2u * A_TILE_BYTES;
-                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = b_base + (uint32_t)sb * b_slot;
-                    const uint32_t b_lo = b_hi + n_tile * 128;
-                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-                    if (p.precision == 0) {
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k)
-                            umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k)
-                            umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(empty_a(sa));
-                    umma_commit(empty_b(sb));
-                    if (++sa == SA) { sa = 0; pha ^= 1; }
-                    if (++sb == SB) { sb = 0; phb ^= 1; }
-                }
-                umma_commit(tmem_full(acc));
-            }
-        }
-    } else if (warp < 10) {
-        // ===================== activation producers (2 groups x 4 warps), cp.async landing ring =====================
-        const int pt = threadIdx.x - 64;
-        const int grp = pt >> 7;
-        const int t = pt & 127;
-        const int chunk = t & 7;
-        const int r0 = t >> 3;
-        const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
-        const int xs = (int)p.xs;
-        const int KC = p.KC, KW = p.KW, KH = p.KH, dil = p.dil, Cin = p.Cin, Ws = p.Ws;
-        constexpr bool AFF = PRE >= 2;
-        constexpr bool RELU = (PRE & 1) != 0;
-        const float *__restrict__ xg = p.x;
-        const uint32_t roff0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);
-        const int c0 = chunk * 4;
-        const int D = R >> 1;                              // landing slots (= k-blocks in flight) of this group
-        const uint32_t my_raw = r_base + (uint32_t)grp * RAW_BYTES + (uint32_t)t * 16u;   // + slot * 2*RAW + i * 2048
-        int oy[8], ox[8], rowoff[8];
-        int l_ti = 0, l_ky = 0, l_kx = 0, l_kc = 0, cur_ti = -1;
-        auto advance = [&]() {
-            if (++l_kc == KC) {
-                l_kc = 0;
-                if (++l_kx == KW) {
-                    l_kx = 0;
-                    if (++l_ky == KH) { l_ky = 0; ++l_ti; }
-                }
-            }
-        };
-        if (grp) advance();
-        auto set_tile = [&](int ti) {
-            cur_ti = ti;
-            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-            const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntiles);
-            const uint32_t m_base = m_tile * BLOCK_M + (uint32_t)r0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t m = m_base + 16u * i;
-                if ((long long)m < p.M) {
-                    const uint32_t q = fdiv(m, p.fd_wout);
-                    const int x = (int)(m - q * (uint32_t)p.Wout);
-                    const uint32_t b = fdiv(q, p.fd_hout);
-                    const int y = (int)(q - b * (uint32_t)p.Hout);
-                    oy[i] = y * p.stride - p.pad;
-                    ox[i] = x * p.stride - p.pad;
-                    rowoff[i] = (int)b * p.Hs * Ws * xs + (UP ? 0 : (oy[i] * Ws + ox[i]) * xs);
-                } else {
-                    oy[i] = ox[i] = -0x40000000;
-                    rowoff[i] = 0;
-                }
-            }
-        };
-        uint32_t maskq = 0;                                // validity masks of the k-blocks in flight (8 bits each)
-        int l_slot = 0;                                    // landing slot of the next issue (0..D-1)
-        auto issue = [&](bool real) {
-            uint32_t mk = 0;
-            if (real) {
-                if (l_ti != cur_ti) set_tile(l_ti);
-                const int dy = l_ky * dil, dx = l_kx * dil;
-                const int c = l_kc * 32 + c0;
-                const bool cok = c < Cin;
-                const int tapoff = UP ? c : (dy * Ws + dx) * xs + c;
-                const uint32_t dst = my_raw + (uint32_t)l_slot * (2u * RAW_BYTES);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int yy = oy[i] + dy, xx = ox[i] + dx;
-                    const bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
-                    mk |= (ok ? 1u : 0u) << i;
-                    int off;
-                    if (UP) off = rowoff[i] + ((yy >> 1) * Ws + (xx >> 1)) * xs + tapoff;
-                    else off = rowoff[i] + tapoff;
-                    cp_async16_ca(dst + (uint32_t)i * 2048u, xg + (ok ? off : 0), ok ? 16u : 0u);   // zero-fill when !ok
-                }
-                advance();
-                advance();
-            }
-            cp_async_commit();                             // one group per push (possibly empty) keeps the count uniform
-            maskq = (maskq << 8) | mk;
-            if (++l_slot == D) l_slot = 0;
-        };
-        int s_s = grp;                                     // A stage of this group's next store (SA >= 2)
-        uint32_t s_ph = 0;
-        int s_kc = grp;
-        while (s_kc >= KC) s_kc -= KC;
-        int c_slot = 0;
-        const uint32_t mshift = 8u * (uint32_t)(D - 1);
-        auto convert = [&]() {
-            cp_async_wait_dyn(D - 1);                      // the oldest k-block in flight has landed
-            const uint32_t src = my_raw + (uint32_t)c_slot * (2u * RAW_BYTES);
-            if (++c_slot == D) c_slot = 0;
-            const uint32_t mask = (maskq >> mshift) & 0xffu;
-            F4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 q = ld_shared_v4(src + (uint32_t)i * 2048u);
-                v[i].v[0] = q.x; v[i].v[1] = q.y; v[i].v[2] = q.z; v[i].v[3] = q.w;
-            }
-            const int c = s_kc * 32 + c0;
-            const uint32_t a_hi = a_base + (uint32_t)s_s * 2u * A_TILE_BYTES + roff0;
-            const uint32_t a_lo = a_hi + A_TILE_BYTES;
-            const uint32_t bar_full = full_a(s_s);
-            const uint32_t bar_empty = empty_a(s_s);
-            const uint32_t ph = s_ph ^ 1;
-            s_s += 2;
-            if (s_s >= SA) { s_s -= SA; s_ph ^= 1; }
-            s_kc += 2;
-            while (s_kc >= KC) s_kc -= KC;
-            float sc[4], sh[4];
-            if (AFF) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(s_scale + c);
-                const float4 b4 = *reinterpret_cast<const float4 *>(s_shift + c);
-                sc[0] = a4.x; sc[1] = a4.y; sc[2] = a4.z; sc[3] = a4.w;
-                sh[0] = b4.x; sh[1] = b4.y; sh[2] = b4.z; sh[3] = b4.w;
-            }
-            if (c < Cin && c + 3 >= Cin) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int e = 1; e < 4; ++e)
-                        if (c + e >= Cin) v[i].v[e] = 0.f;
-            }
-            float hi[8][4], lo[8][4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool live = (mask >> i) & 1u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float a = v[i].v[e];
-                    if (AFF) {
-                        a = fmaf(a, sc[e], sh[e]);
-                        if (RELU) a = fmaxf(a, 0.f);
-                        a = live ? a : 0.f;
-                    } else if (RELU) {
-                        a = fmaxf(a, 0.f);
-                    }
-                    const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
-                    hi[i][e] = h;
-                    lo[i][e] = a - h;
-                }
-            }
-            mbar_wait(bar_empty, ph);                      // the MMAs that read this stage two k-blocks ago are done
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                st_shared_v4(a_hi + (uint32_t)i * 2048u, hi[i][0], hi[i][1], hi[i][2], hi[i][3]);
-                st_shared_v4(a_lo + (uint32_t)i * 2048u, lo[i][0], lo[i][1], lo[i][2], lo[i][3]);
-            }
-            fence_proxy_async();
-            mbar_arrive(bar_full);
-        };
-        {
-            const int mine = (total_kb - grp + 1) >> 1;    // k-blocks of this group
-            int issued = 0;
-            for (int d = 0; d < D; ++d) { issue(issued < mine); ++issued; }
-            for (int done = 0; done < mine; ++done) {
-                convert();
-                issue(issued < mine);
-                ++issued;
-            }
-            cp_async_wait_dyn(0);
-        }
-    } else {
-        // ===================== epilogue warps (10..13) =====================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0);
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-            const int m_tile = (int)fdiv((uint32_t)tile, p.fd_ntiles), nt = tile - m_tile * p.n_tiles;
-            const int acc = ti & 1;
-            const long long m = (long long)m_tile * BLOCK_M + row;
-            float *orow = p.out + (m < p.M ? m : 0) * p.os + (long long)nt * n_tile;
-            mbar_wait_sleep(tmem_full(acc), (uint32_t)((ti >> 1) & 1));
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128);
-            for (int cc = 0; cc < n_tile; cc += 16) {
-                uint32_t r[16];
-                tmem_ld8(t_addr + (uint32_t)cc, reinterpret_cast<uint32_t(&)[8]>(r[0]));
-                tmem_ld8(t_addr + (uint32_t)cc + 8, reinterpret_cast<uint32_t(&)[8]>(r[8]));
-                tmem_ld_wait();
-                if (m < p.M) {
-                    const int cbase = nt * n_tile + cc;
-#pragma unroll
-                    for (int e4 = 0; e4 < 16; e4 += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float a = __uint_as_float(r[e4 + e]);
-                            if (p.act == 1) a = a > 0.f ? a : expm1f(a);
-                            else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
-                            o[e] = a;
-                        }
-                        if (ovec && cbase + e4 + 3 < p.Cout) {
-                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = o[e];
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(tmem_empty(acc));
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------- C ABI
 extern "C" int bts_conv_n_tile(int Cout) {
     int n = (Cout + 15) / 16 * 16;
     if (n > MAX_N) {
-        // split into equal tiles <= 128, multiples of 16
+        // split into equal tiles <= 256, multiples of 16
         const int tiles = (n + MAX_N - 1) / MAX_N;
         n = ((Cout + tiles - 1) / tiles + 15) / 16 * 16;
     }
@@ -881,57 +571,6 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
     cudaError_t err = cudaSuccess;
-    // ---- async-producer plan (cp.async landing ring + separate weight ring); needs 16-byte aligned rows
-    {
-        static int mode = -1, f_sa = 0, f_sb = 0, f_ring = 0;
-        if (mode < 0) {
-            const char *e = getenv("BTS_B200_CONV_ASYNC");        // 0: register-prefetch kernel only
-            mode = (e && e[0] == '0') ? 0 : 1;
-            const char *pl = getenv("BTS_B200_CONV_PLAN");        // "sa,sb,ring" override for sweeps
-            if (pl) sscanf(pl, "%d,%d,%d", &f_sa, &f_sb, &f_ring);
-        }
-        if (mode == 1 && vec) {
-            const int b_slot = 2 * p.n_tile * 128;
-            const int budget = SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes;
-            int sa = f_sa ? f_sa : 2, ring = f_ring ? f_ring : 6, sb = 0;
-            for (;;) {
-                sb = (budget - sa * 2 * A_TILE_BYTES - ring * RAW_BYTES) / b_slot;
-                if (sb > MAX_SB) sb = MAX_SB;
-                if (f_sb && sb > f_sb) sb = f_sb;
-                if (sb >= 3 || ring <= 2 || f_ring) break;
-                ring -= 2;                                        // trade landing depth for weight slots
-            }
-            if (sa >= 2 && sa <= MAX_SA && ring >= 4 && ring <= MAX_RING && (ring & 1) == 0 && sb >= 2) {
-                p.sa = sa; p.sb = sb; p.ring = ring;
-                const int smem_async = sa * 2 * A_TILE_BYTES + sb * b_slot + ring * RAW_BYTES + pre_bytes + BAR_BYTES + 1024;
-#define BTS_LAUNCH_ASYNC(PRE, UP)                                                                                  \
-    do {                                                                                                           \
-        static bool attr_set = false;                                                                              \
-        if (!attr_set) {                                                                                           \
-            err = cudaFuncSetAttribute(conv_tc_async_kernel<PRE, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       SMEM_LIMIT);                                                                \
-            if (err != cudaSuccess) return (int)err;                                                               \
-            attr_set = true;                                                                                       \
-        }                                                                                                          \
-        conv_tc_async_kernel<PRE, UP><<<grid, NUM_THREADS, smem_async, (cudaStream_t)stream>>>(p);                 \
-    } while (0)
-#define BTS_DISPATCH_ASYNC(PRE)                                                        \
-    do {                                                                               \
-        if (p.up) BTS_LAUNCH_ASYNC(PRE, true); else BTS_LAUNCH_ASYNC(PRE, false);      \
-    } while (0)
-                switch (pre) {
-                    case 0: BTS_DISPATCH_ASYNC(0); break;
-                    case 1: BTS_DISPATCH_ASYNC(1); break;
-                    case 2: BTS_DISPATCH_ASYNC(2); break;
-                    default: BTS_DISPATCH_ASYNC(3); break;
-                }
-#undef BTS_DISPATCH_ASYNC
-#undef BTS_LAUNCH_ASYNC
-                BTS_LAUNCH_CHECK();
-                return 0;
-            }
-        }
-    }
 #define BTS_LAUNCH(PRE, UP, VEC)                                                                                   \
     do {                                                                                                           \
         static bool attr_set = false;                                                                              \

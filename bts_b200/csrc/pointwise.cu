@@ -1,0 +1,149 @@
+// Weight gradient of the narrow 1x1 convolutions of the reduction heads (reference pytorch/bts.py:83-108:
+// reduc1x1 32->16->8 at full resolution, reduc2x2 64->32->16->8->3 at half resolution, ...) as an HBM-bound CUDA-core
+// kernel, sm_100a.
+//
+//   dW[co, ci] = sum_p dY[p, co] * x[p, ci]            Cin in {8,16,32,64}, Cout <= 32, NHWC operands
+//
+// On the tensor-core wgrad these layers fill 32 (or 8) of the 128 TMEM lanes and 16 (or 3) of the columns and still
+// pay the full operand-staging pipeline: round-1 trace 1.65 ms for 16->8 at 352x704x16 against 0.06 ms of HBM time.
+// Here a lane owns one (or two) input channels of one pixel slot and keeps all Cout accumulators in registers:
+// the x row of a pixel is one coalesced load, the dY row a broadcast load; pixel slots of a warp, warps of a block and
+// blocks are combined in a fixed order (shuffles, shared memory, a second pass over per-block partials) -> deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PW_THREADS = 256;
+constexpr int PW_MAXCO = 32;
+
+struct PwParams {
+    const float *x; long long xs;
+    const float *dy; long long dys;
+    long long M;
+    int Cin, Cout;
+    float *part;              // [gridDim.x][Cin][Cout]
+};
+
+// CL = lanes per pixel (min(Cin, 32)), R = channels per lane (Cin / CL), CO = Cout rounded up to a multiple of 4
+template <int CL, int R, int CO>
+__global__ void __launch_bounds__(PW_THREADS) pw_wgrad_kernel(const PwParams p) {
+    constexpr int PP = 32 / CL;                            // pixel slots per warp iteration
+    __shared__ float red[PW_THREADS / 64][CL * R * CO];     // <= 4 x 2048 floats = 32 KB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = lane % CL, slot = lane / CL;
+    float acc[R][CO];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[r][c] = 0.f;
+    const long long nwarps = (long long)gridDim.x * (PW_THREADS / 32);
+    const long long w0 = (long long)blockIdx.x * (PW_THREADS / 32) + warp;
+    const bool dvec = ((p.dys & 3) == 0) && ((((uintptr_t)p.dy) & 15) == 0) && (p.Cout % 4 == 0);
+    for (long long pix = w0 * PP + slot; pix < p.M; pix += nwarps * PP) {
+        float xv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) xv[r] = __ldg(p.x + pix * p.xs + ci + r * CL);
+        float g[CO];
+        const float *drow = p.dy + pix * p.dys;
+        if (dvec) {
+#pragma unroll
+            for (int c = 0; c < CO; c += 4) {
+                if (c < p.Cout) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(drow + c));
+                    g[c] = q.x; g[c + 1] = q.y; g[c + 2] = q.z; g[c + 3] = q.w;
+                } else {
+                    g[c] = g[c + 1] = g[c + 2] = g[c + 3] = 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CO; ++c) g[c] = c < p.Cout ? __ldg(drow + c) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[r][c] = fmaf(xv[r], g[c], acc[r][c]);
+    }
+    // pixel slots of the warp (lane bits above log2 CL), fixed butterfly order
+#pragma unroll
+    for (int m = CL; m < 32; m <<= 1)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[r][c] += __shfl_xor_sync(0xffffffffu, acc[r][c], m);
+    // warps of the block: the upper four park their sums, the lower four add them to their own and park the result
+    constexpr int HW = PW_THREADS / 64;
+    if (slot == 0 && warp >= HW) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) red[warp - HW][(ci + r * CL) * CO + c] = acc[r][c];
+    }
+    __syncthreads();
+    if (slot == 0 && warp < HW) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) red[warp][(ci + r * CL) * CO + c] += acc[r][c];
+    }
+    __syncthreads();
+    const int n = CL * R * CO;
+    for (int i = threadIdx.x; i < n; i += PW_THREADS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < HW; ++wv) sum += red[wv][i];
+        const int c = i % CO, cin = i / CO;
+        if (c < p.Cout) p.part[((size_t)blockIdx.x * p.Cin + cin) * p.Cout + c] = sum;
+    }
+}
+
+__global__ void pw_wgrad_reduce(const float *__restrict__ part, int nblocks, int Cin, int Cout, float *__restrict__ dw,
+                                long long s_co, long long s_ci) {
+    const int n = Cin * Cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float sum = 0.f;
+        for (int b = 0; b < nblocks; ++b) sum += part[(size_t)b * n + i];
+        const int ci = i / Cout, co = i - ci * Cout;
+        dw[co * s_co + ci * s_ci] = sum;
+    }
+}
+
+int pw_grid() { return bts_num_sms() * 4; }
+
+}  // namespace
+
+extern "C" int bts_conv_pw_wgrad_eligible(int Cin, int Cout) {
+    return (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && Cout >= 1 && Cout <= PW_MAXCO;
+}
+
+extern "C" long long bts_conv_pw_wgrad_workspace_floats(int Cin, int Cout) { return (long long)pw_grid() * Cin * Cout; }
+
+extern "C" int bts_conv_pw_wgrad(const float *x, long long x_pixel_stride, const float *dy, long long dy_pixel_stride,
+                                 long long M, int Cin, int Cout, float *workspace, float *dw, long long s_co,
+                                 long long s_ci, void *stream) {
+    if (!x || !dy || !workspace || !dw || M < 1 || !bts_conv_pw_wgrad_eligible(Cin, Cout)) return BTS_EINVAL;
+    PwParams p;
+    p.x = x; p.xs = x_pixel_stride; p.dy = dy; p.dys = dy_pixel_stride; p.M = M; p.Cin = Cin; p.Cout = Cout;
+    p.part = workspace;
+    const int grid = pw_grid();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int co4 = (Cout + 3) / 4 * 4;
+#define BTS_PW(CL, R)                                                                                   \
+    switch (co4) {                                                                                      \
+        case 4: pw_wgrad_kernel<CL, R, 4><<<grid, PW_THREADS, 0, st>>>(p); break;                       \
+        case 8: pw_wgrad_kernel<CL, R, 8><<<grid, PW_THREADS, 0, st>>>(p); break;                       \
+        case 12: case 16: pw_wgrad_kernel<CL, R, 16><<<grid, PW_THREADS, 0, st>>>(p); break;            \
+        default: pw_wgrad_kernel<CL, R, 32><<<grid, PW_THREADS, 0, st>>>(p); break;                     \
+    }
+    switch (Cin) {
+        case 8: BTS_PW(8, 1) break;
+        case 16: BTS_PW(16, 1) break;
+        case 32: BTS_PW(32, 1) break;
+        default: BTS_PW(32, 2) break;
+    }
+#undef BTS_PW
+    BTS_LAUNCH_CHECK();
+    pw_wgrad_reduce<<<(Cin * Cout + 127) / 128, 128, 0, st>>>(workspace, grid, Cin, Cout, dw, s_co, s_ci);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}

@@ -33,6 +33,7 @@ struct W2Params {
     const float *dy; long long dys;
     int Cout, Hout, Wout, Hin, Win;
     int cg, nb;              // output channels per CTA (multiple of 16, <= 48) and their 32-channel chunks
+    int nchunks;             // 32-slot chunks of the tap-packed dY tile: ceil(taps*cg/32)
     float *part;             // [splitK][taps][Cin][Cout]
     int splitK, kb_per_split, KBq;
     int Mq;                  // B*Hin*Win input pixels
@@ -61,8 +62,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
     const int co0 = cgi * p.cg;
     const int ncol = min(p.cg, ((p.Cout - co0 + 15) >> 4) << 4);     // live columns of this CTA (multiple of 16)
     const int nb = p.nb;
-    const uint32_t b_tap = (uint32_t)nb * CHUNK;                     // bytes of one tap's dY tile (hi or lo)
-    const uint32_t b_half = (uint32_t)taps * b_tap;
+    // dY operand: the taps are packed DENSELY along N -- tap t owns the N slots [t*ncol, (t+1)*ncol) of one long MN-major
+    // tile of ceil(taps*ncol/32) chunks -- so that a single tcgen05.mma (N up to 256) multiplies the activation tile
+    // against many taps at once (see the MMA issuer).  hi and lo tiles follow each other.
+    const int n_total = taps * ncol;
+    const uint32_t b_half = (uint32_t)p.nchunks * CHUNK;
     const int kb0 = split * p.kb_per_split;
     int kb1 = kb0 + p.kb_per_split;
     if (kb1 > p.KBq) kb1 = p.KBq;
@@ -94,10 +98,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
 
     if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BLOCK_CI, ncol, 1, 1);
+            // A tcgen05.mma with M=128, K=8 costs ~115-130 cycles whatever N is (round-1 measurement: 54 per-tap MMAs
+            // per 16-pixel k-block = 5.5k cycles, exactly the observed k-block time).  With the taps packed along N the
+            // three products of a k-group are 3 x ceil(taps*ncol/256) instructions instead of 3 x taps.
+            const int n0 = n_total < 256 ? n_total : 256, n1 = n_total - n0;        // multiples of 16
+            const uint32_t idesc0 = make_idesc(BLOCK_CI, n0, 1, 1);
+            const uint32_t idesc1 = make_idesc(BLOCK_CI, n1 > 0 ? n1 : 16, 1, 1);
             const uint64_t dah0 = make_desc_mn(base, CHUNK), dal0 = make_desc_mn(base + A_BYTES, CHUNK);
             const uint64_t dbh0 = make_desc_mn(base + 2 * A_BYTES, CHUNK), dbl0 = make_desc_mn(base + 2 * A_BYTES + b_half, CHUNK);
-            const uint64_t tap_step = (uint64_t)(b_tap >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
+            const uint64_t piece1 = (uint64_t)((8 * CHUNK) >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
             int s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
@@ -108,16 +117,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                 for (int kg = 0; kg < KP / 8; ++kg) {
                     const uint64_t o = so + (uint64_t)(kg * (1024 >> 4));   // start-address field: + 1024 B per k-group
                     const uint32_t accumulate = (it | kg) != 0;
-                    uint64_t ob = o;
-                    uint32_t d = tmem_base;
-                    for (int t = 0; t < taps; ++t, ob += tap_step, d += (uint32_t)ncol) {
-                        if (p.precision == 0) {
-                            umma_tf32(d, dal0 + o, dbh0 + ob, idesc, accumulate);
-                            umma_tf32(d, dah0 + o, dbl0 + ob, idesc, 1);
-                            umma_tf32(d, dah0 + o, dbh0 + ob, idesc, 1);
-                        } else {
-                            umma_tf32(d, dah0 + o, dbh0 + ob, idesc, accumulate);
+                    if (p.precision == 0) {
+                        umma_tf32(tmem_base, dal0 + o, dbh0 + o, idesc0, accumulate);
+                        umma_tf32(tmem_base, dah0 + o, dbl0 + o, idesc0, 1);
+                        umma_tf32(tmem_base, dah0 + o, dbh0 + o, idesc0, 1);
+                        if (n1 > 0) {
+                            umma_tf32(tmem_base + 256, dal0 + o, dbh0 + o + piece1, idesc1, accumulate);
+                            umma_tf32(tmem_base + 256, dah0 + o, dbl0 + o + piece1, idesc1, 1);
+                            umma_tf32(tmem_base + 256, dah0 + o, dbh0 + o + piece1, idesc1, 1);
                         }
+                    } else {
+                        umma_tf32(tmem_base, dah0 + o, dbh0 + o, idesc0, accumulate);
+                        if (n1 > 0) umma_tf32(tmem_base + 256, dah0 + o, dbh0 + o + piece1, idesc1, accumulate);
                     }
                 }
                 umma_commit(empty(s));
@@ -169,6 +180,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             toy[j] = ky * p.dil - p.pad;
             tox[j] = kx * p.dil - p.pad;
         }
+        // shared-memory offsets of this thread's dY units in the densely packed tile: N slot = t*ncol + channel
+        uint32_t boff[NBU];
+        bool blive[NBU];
+#pragma unroll
+        for (int j = 0; j < NBU / 2; ++j)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int t = half + 4 * j;
+                const int c = unit * 4 + ch * 32;                         // channel within this CTA's group
+                const int n = t * ncol + c;
+                blive[j * 2 + ch] = t < taps && ch < nb && c < ncol;
+                boff[j * 2 + ch] = (uint32_t)(n >> 5) * CHUNK + mn_swizzle_off(row, (n & 31) >> 2);
+            }
         auto load = [&](int it, F4(&va)[NAU], F4(&vb)[NBU], bool &okx) {
             const int q = (kb0 + it) * KP + row;
             okx = q < p.Mq;
@@ -277,17 +301,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                 split_store(a_hi + o, a_lo + o, va[ch]);
             }
 #pragma unroll
-            for (int j = 0; j < NBU / 2; ++j) {
-                const int t = half + 4 * j;
-                if (t < taps) {
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch)
-                        if (ch < nb) {
-                            const uint32_t o = (uint32_t)t * b_tap + (uint32_t)ch * CHUNK + roff;
-                            split_store(b_hi + o, b_lo + o, vb[j * 2 + ch]);
-                        }
-                }
-            }
+            for (int j = 0; j < NBU; ++j)
+                if (blive[j]) split_store(b_hi + boff[j], b_lo + boff[j], vb[j]);
             fence_proxy_async();
             mbar_arrive(full(s));
         };
@@ -359,7 +374,7 @@ int bts_wgrad2_cg(int Cout, int taps) {
 // loses for Cout = 64 (two co groups re-produce the activation tile) and on the small maps of blocks 3-4
 bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq) {
     const int taps = KH * KW;
-    return taps > 1 && taps <= MAX_TAPS && Cout <= 48 && stride == 1 && Mq >= 60000 && bts_wgrad2_cg(Cout, taps) > 0;
+    return taps > 1 && taps <= MAX_TAPS && Cout <= 64 && stride == 1 && Mq >= 60000 && bts_wgrad2_cg(Cout, taps) > 0;
 }
 
 void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK) {
@@ -403,7 +418,8 @@ int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int u
     p.Mq = (int)Mq;
     p.KBq = (int)((Mq + KP - 1) / KP);
     p.kb_per_split = (p.KBq + splitK - 1) / splitK;
-    p.stage_bytes = 2 * A_BYTES + 2 * taps * p.nb * CHUNK;
+    p.nchunks = (taps * p.cg + 31) / 32;
+    p.stage_bytes = 2 * A_BYTES + 2 * p.nchunks * CHUNK;
     p.stages = SMEM_BUDGET / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return BTS_EINVAL;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
     if (p.pre_scale) {
         for (int c = threadIdx.x; c < BLOCK_CI; c += NUM_THREADS) {
             const int ch = ci_tile * BLOCK_CI + c;
@@ -96,22 +96,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
 
     if (warp == 1) {
         if (lane == 0) {
+            // 2 MMAs per k-group instead of 3 (a tcgen05.mma with M=128, K=8 costs ~120 cycles whatever N is): the dY_lo
+            // chunks follow the dY_hi chunks in the stage, so one instruction with N = 32*nchunk + n_tile computes
+            // x_hi^T * [dY_hi ; dY_lo]; the epilogue adds the column blocks [0,n_tile) and [32*nchunk, 32*nchunk+n_tile).
+            const int nchunk_b = (n_tile + 31) >> 5;
             const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
+            const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(full(s), ph);
                 tc_fence_after();
                 const uint32_t a_hi = base + s * Smem::STAGE_BYTES, a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + MAX_N * 128;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + (uint32_t)nchunk_b * CHUNK_BYTES;
 #pragma unroll
                 for (int kg = 0; kg < BLOCK_KP / 8; ++kg) {
                     const uint64_t dah = make_desc_mn(a_hi + kg * 1024, CHUNK_BYTES), dal = make_desc_mn(a_lo + kg * 1024, CHUNK_BYTES);
                     const uint64_t dbh = make_desc_mn(b_hi + kg * 1024, CHUNK_BYTES), dbl = make_desc_mn(b_lo + kg * 1024, CHUNK_BYTES);
                     if (p.precision == 0) {
-                        umma_tf32(tmem_base, dal, dbh, idesc, (it | kg) != 0);
-                        umma_tf32(tmem_base, dah, dbl, idesc, 1);
-                        umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                        (void)dbl;
+                        umma_tf32(tmem_base, dah, dbh, idesc2, (it | kg) != 0);   // x_hi * [dY_hi ; dY_lo]
+                        umma_tf32(tmem_base, dal, dbh, idesc, 1);                 // x_lo * dY_hi
                     } else {
                         umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
                     }
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty(s), ph ^ 1);
                 const uint32_t t_hi = base + s * Smem::STAGE_BYTES + 2 * A_BYTES;
-                split_store(t_hi, t_hi + MAX_N * 128, v, nchunk);
+                split_store(t_hi, t_hi + (uint32_t)nchunk * CHUNK_BYTES, v, nchunk);
                 fence_proxy_async();
                 mbar_arrive(full(s));
             };
@@ -333,10 +338,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         const int taps = p.KH * p.KW;
         float *prow = p.part + (((long long)split * taps + tap) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + (long long)nt * n_tile;
         const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0);
+        const int lo_col = ((n_tile + 31) >> 5) * 32;       // first accumulator column of the x_hi * dY_lo block
         for (int cc = 0; cc < half; cc += 8) {
             uint32_t r[8];
             tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cc), r);
-            tmem_ld_wait();
+            if (p.precision == 0) {
+                uint32_t r2[8];
+                tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(lo_col + col0 + cc), r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            } else {
+                tmem_ld_wait();
+            }
             if (ci < p.Cin) {
                 const int cbase = nt * n_tile + col0 + cc;
 #pragma unroll
@@ -357,7 +371,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 128);
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 // dW[co,ci,kh,kw] (arbitrary strides) = sum_split part[split][tap][ci][co]; fixed summation order -> deterministic
@@ -379,7 +393,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 
 }  // namespace
 
-extern "C" int bts_conv_n_tile(int Cout);
+// N tile of the wgrad kernels (their shared-memory plan holds <= 128 output channels per CTA)
+static int wgrad_n_tile(int Cout) {
+    int n = (Cout + 15) / 16 * 16;
+    if (n > MAX_N) {
+        const int tiles = (n + MAX_N - 1) / MAX_N;
+        n = ((Cout + tiles - 1) / tiles + 15) / 16 * 16;
+    }
+    return n;
+}
 
 // narrow-output 3x3 layers use the shifted-dY kernel (wgrad2_tc.cu)
 bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq);
@@ -401,7 +423,7 @@ extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout,
     }
     const long long M = (long long)B * Hout * Wout;
     const long long KBp = (M + BLOCK_KP - 1) / BLOCK_KP;
-    const int n_tile = bts_conv_n_tile(Cout);
+    const int n_tile = wgrad_n_tile(Cout);
     const long long tiles = (long long)((Cin + BLOCK_CI - 1) / BLOCK_CI) * ((Cout + n_tile - 1) / n_tile) * KH * KW;
     const int sms = bts_num_sms();
     // split-K so that the CTA count fills whole waves of the SMs (a 297-CTA grid on 148 SMs wastes a third of the
@@ -444,7 +466,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     if (p.Hout < 1 || p.Wout < 1 || M > 0x7ffffff0LL) return BTS_EINVAL;
     if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL || M * dy_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;
     p.M = (int)M;
-    p.n_tile = bts_conv_n_tile(Cout);
+    p.n_tile = wgrad_n_tile(Cout);
     p.part = workspace; p.splitK = splitK;
     p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
     p.kb_per_split = (p.KBp + splitK - 1) / splitK;

@@ -193,6 +193,14 @@ int bts_avgpool2_fwd(const float *x, long long x_pixel_stride, int B, int Hout, 
 int bts_avgpool2_bwd(const float *g, long long g_pixel_stride, int B, int Hout, int Wout, int C, float *gx,
                      long long gx_pixel_stride, void *stream);
 
+/* ---- weight gradient of the narrow 1x1 convolutions of the reduction heads (bts.py:83-108) on CUDA cores (csrc/pointwise.cu):
+ * dW[co,ci] = sum_p dY[p,co]*x[p,ci] for Cin in {8,16,32,64}, Cout <= 32 -- HBM-bound, deterministic two-pass reduction.
+ * workspace: bts_conv_pw_wgrad_workspace_floats(Cin, Cout) floats; dw addressed by its (co, ci) strides in floats. */
+int bts_conv_pw_wgrad_eligible(int Cin, int Cout);
+long long bts_conv_pw_wgrad_workspace_floats(int Cin, int Cout);
+int bts_conv_pw_wgrad(const float *x, long long x_pixel_stride, const float *dy, long long dy_pixel_stride, long long M,
+                      int Cin, int Cout, float *workspace, float *dw, long long s_co, long long s_ci, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

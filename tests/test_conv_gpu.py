@@ -165,3 +165,26 @@ def test_wgrad_narrow_output_shifted_dy_kernel(Cin, Cout, H, W, dil, up, pre):
                        upsample2=up)
     err = (gw.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("Cin,Cout", [(32, 16), (16, 8), (8, 3), (64, 32), (64, 12), (8, 1)])
+def test_pointwise_wgrad_cuda_core_kernel(Cin, Cout, monkeypatch):
+    """narrow 1x1 layers of the reduction heads: dW on the HBM-bound CUDA-core kernel (csrc/pointwise.cu) vs fp64"""
+    from bts_b200 import _lib, conv
+    monkeypatch.setattr(conv, "PW_MIN_PIXELS", 0)
+    assert _lib.lib().bts_conv_pw_wgrad_eligible(Cin, Cout)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, Cin, 17, 23, generator=g)
+    gy = torch.randn(3, Cout, 17, 23, generator=g)
+    ref = torch.einsum("bohw,bihw->oi", gy.double(), x.double()).reshape(Cout, Cin, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    for gyc in (gy.cuda().contiguous(memory_format=torch.channels_last), gy.cuda()):      # NHWC and NCHW upstream grads
+        before = len(conv.trace_log)
+        gw = conv.wgrad_tc(xc, gyc, (Cout, Cin, 1, 1), (Cin, 1, 1, 1), 1, 0, 1)
+        err = (gw.cpu().double() - ref).abs().max() / ref.abs().max()
+        assert err < 1e-5, float(err)
+    # a channel slice of a wider slab as the activation operand
+    slab = torch.randn(3, Cin + 8, 17, 23, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    gw = conv.wgrad_tc(slab[:, 4:4 + Cin], gy.cuda(), (Cout, Cin, 1, 1), (Cin, 1, 1, 1), 1, 0, 1)
+    ref2 = torch.einsum("bohw,bihw->oi", gy.double(), slab[:, 4:4 + Cin].cpu().double()).reshape(Cout, Cin, 1, 1)
+    assert (gw.cpu().double() - ref2).abs().max() / ref2.abs().max() < 1e-5
