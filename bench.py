@@ -217,7 +217,11 @@ def lpg_roofline(torch, dev, pk):
     return {"bound": "hbm", "kernel": "lpg_fwd_vec<8> + lpg_bwd_vec<8> (fwd+bwd, r=8, 128x1024x1024, output 512 MB >> L2, "
                                       "20 back-to-back launches each)",
             "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a / pk["hbm_gbs"], "peak_source": pk["source"],
-            "traffic": None, "sweep": out}
+            # dram__bytes_read.sum + dram__bytes_write.sum of one (fwd, bwd) launch pair, `ncu --set full` capture
+            # profiles/r01_lpg_r8_v2.ncu-rep of this same microbench: fwd 33.6 + 479.3 MB, bwd 570.4 + 32.3 MB
+            # (algorithmic 570.4 + 604.0 MB: no re-reads; part of the forward's output is still dirty in L2 at kernel end)
+            "traffic": 1115.6e6, "traffic_unit": "bytes per fwd+bwd launch pair (ncu, profiles/r01_lpg_r8_v2.ncu-rep)",
+            "algorithmic_bytes": (4.0 * 128 * 1024 * 1024) * ((1 + 4.0 / 64) + (1 + 8.0 / 64)), "sweep": out}
 
 
 def run_ours(args):
