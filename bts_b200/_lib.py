@@ -77,6 +77,7 @@ SIGNATURES = {
     "bts_conv_packed_floats": [_i, _i, _i, _i],
     "bts_conv_pack_weights": [_p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _p],
     "bts_conv_fwd": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _ll, _i, _i, _p],
+    "bts_conv_fwd_stats": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _ll, _i, _i, _p, _p, _p],
     "bts_conv_wgrad_plan": [_i, _i, _i, _i, _i, _i, _i, _p, _p],
     "bts_conv_wgrad": [_p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _ll, _i, _p, _i, _p, _ll, _ll,
                        _ll, _ll, _i, _p],

@@ -89,9 +89,12 @@ def _nhwc_view(x):
 
 
 def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_shift=None, pre_relu=False,
-              upsample2=False, act=None, out=None, precision=0, packed=None, cout=None, transpose_flip=False):
+              upsample2=False, act=None, out=None, precision=0, packed=None, cout=None, transpose_flip=False,
+              stats=None):
     """Runs the engine.  x: (B,Cin,Hs,Ws) NHWC-in-memory fp32 CUDA.  Returns (B,Cout,Hout,Wout) channels_last.
-    `out` may be a pre-allocated channels_last tensor or a channel slice of one (concat-free writes)."""
+    `out` may be a pre-allocated channels_last tensor or a channel slice of one (concat-free writes).
+    `stats`: a ZEROED fp64 [2, Cout] tensor that receives per-channel (sum, sum of squares) of the output, reduced in the
+    conv epilogue (Cout <= 256) -- the BatchNorm batch statistics of the tensor being produced."""
     _need_cuda(x, weight)
     if x.dtype != torch.float32:
         raise TypeError("conv2d_tc computes in fp32 (3xTF32 on tcgen05); got %s" % x.dtype)
@@ -121,11 +124,20 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
         pre_scale = pre_scale.contiguous()
         pre_shift = pre_shift.contiguous()
     with torch.cuda.device(x.device):
+        if stats is None:
+            call = lambda: _lib.lib().bts_conv_fwd(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
+                                                   dilation, _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift),
+                                                   int(pre_relu), _ptr(out), os_, ACT[act], int(precision), _stream())
+        else:
+            if stats.dtype != torch.float64 or tuple(stats.shape) != (2, Co) or not stats.is_contiguous():
+                raise ValueError("stats must be a contiguous fp64 [2, Cout] tensor")
+            call = lambda: _lib.lib().bts_conv_fwd_stats(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride,
+                                                         padding, dilation, _ptr(packed), Co, _ptr(pre_scale),
+                                                         _ptr(pre_shift), int(pre_relu), _ptr(out), os_, ACT[act],
+                                                         int(precision), _ptr(stats[0]), _ptr(stats[1]), _stream())
         rc = _traced("dgrad" if transpose_flip else "fwd",
                      "%dx%dx%d %d->%d k%d d%d s%d%s" % (B, Hs, Ws, Cin, Co, KH, dilation, stride, " up" if upsample2 else ""),
-                     lambda: _lib.lib().bts_conv_fwd(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
-                                                     dilation, _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift),
-                                                     int(pre_relu), _ptr(out), os_, ACT[act], int(precision), _stream()))
+                     call)
     _lib.check(rc, "bts_conv_fwd")
     _lib.count()
     return out

@@ -69,7 +69,10 @@ struct ConvParams {
     long long M;             // B*Hout*Wout
     int m_tiles, total_tiles;
     int KC;                  // ceil(Cin/32)
-    int KB;                  // KH*KW*KC k-blocks
+    int CQ;                  // ceil(Cin/4): 16-byte channel quads per tap (dense-K order, see the pack kernel)
+    int KB;                  // ceil(KH*KW*CQ / 8) k-blocks
+    tc::FastDiv fd_cq, fd_kw;
+    double *stat_sum, *stat_sumsq;   // optional per-output-channel sum / sum of squares of the (activated) output
     int stages, stage_bytes; // smem ring: as many (A hi/lo + B hi/lo) stages as fit
     tc::FastDiv fd_wout, fd_hout, fd_ntiles;
 };
@@ -79,7 +82,11 @@ using namespace tc;
 // ------------------------------------------------------------------------------------------- weight packing
 // wpack layout: [n_tiles][KB][2 (hi,lo)][n_tile rows][32 floats], each row 128 B with the 16-byte chunk index
 // XOR-ed by (row & 7) -- exactly the shared-memory image of a K-major SWIZZLE_128B tile, so one contiguous bulk
-// copy per k-block lands it.  k-block order: tap-major, then 32-channel chunk.
+// copy per k-block lands it.
+// K order ("dense K"): the K axis is the sequence of 16-byte channel quads, tap-major: quad g = tap * CQ + c4 with
+// CQ = ceil(Kch / 4); k-block kb holds quads 8 kb .. 8 kb + 7.  A tap therefore costs ceil4(Kch) K-slots instead of
+// ceil32(Kch): conv1 (Cin 36) 11 k-blocks instead of 18, the 3x3 dgrad of the dense layers (48) 14 instead of 18,
+// the 7x7 stem (Cin 3) 7 instead of 49.  Identical to the per-tap 32-channel chunking whenever Kch % 32 == 0.
 // transpose_flip=1 packs the dgrad operator: rows = ci, k = (flipped tap, co).
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
                                                            long long s_kh, long long s_kw, int Cout, int Cin, int KH,
@@ -87,8 +94,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
                                                            int n_tile, int n_tiles) {
     const int Nrows = transpose_flip ? Cin : Cout;    // GEMM N
     const int Kch = transpose_flip ? Cout : Cin;      // GEMM K channels per tap
-    const int KC = (Kch + 31) / 32;
-    const int KB = KH * KW * KC;
+    const int CQ = (Kch + 3) / 4;
+    const int taps = KH * KW;
+    const int KB = (taps * CQ + 7) / 8;
     const long long total = (long long)n_tiles * KB * n_tile * 32;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -98,10 +106,11 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
         t /= n_tile;
         const int kb = (int)(t % KB);
         const int nt = (int)(t / KB);
-        const int tap = kb / KC, kc = kb % KC;
-        const int row = nt * n_tile + n, ch = kc * 32 + kk;
+        const int g = kb * 8 + (kk >> 2);
+        const int tap = g / CQ;
+        const int row = nt * n_tile + n, ch = (g - tap * CQ) * 4 + (kk & 3);
         float val = 0.f;
-        if (row < Nrows && ch < Kch) {
+        if (row < Nrows && tap < taps && ch < Kch) {
             int kh = tap / KW, kw = tap % KW;
             long long off;
             if (transpose_flip) {
@@ -131,6 +140,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
 constexpr int BAR_BYTES = 256;
+constexpr int STAT_BYTES = 2 * MAX_N * 4;   // per-CTA fp32 partial sums of the epilogue statistics
 
 // PRE: 0 none, 1 ReLU, 2 affine, 3 affine + ReLU (compile-time so the per-element producer code carries no dead ops)
 // UP : nearest x2 up-sample folded into the address map;  VEC: 16-byte aligned rows (float4 loads)
@@ -162,10 +172,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
+    float *s_stat = reinterpret_cast<float *>(sm + bar_off + BAR_BYTES);      // [2][MAX_N], only when p.stat_sum
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = p.n_tile;
     const int KB = p.KB;
+    if (p.stat_sum)
+        for (int i = threadIdx.x; i < 2 * MAX_N; i += NUM_THREADS) s_stat[i] = 0.f;
     // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...   (tile -> m_tile = tile / n_tiles, nt = tile % n_tiles)
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * KB;          // host guarantees < 2^31
@@ -277,26 +290,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7  (row & 7 == r0 & 7 for all of them)
         const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
         const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
-        const int KC = p.KC, KW = p.KW, KH = p.KH, dil = p.dil, Cin = p.Cin, Ws = p.Ws;
+        const int KW = p.KW, dil = p.dil, Cin = p.Cin, Ws = p.Ws;
+        const int taps = p.KH * p.KW;
         constexpr bool AFF = PRE >= 2;
         constexpr bool RELU = (PRE & 1) != 0;
         const float *__restrict__ xg = p.x;
         // swizzled byte offset of (row r0 + 16 i, chunk) inside a tile = roff0 + i * 2048
         const uint32_t roff0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);
-        const int c0 = chunk * 4;
-        // ---- LOAD cursor: (tile iteration, tap row/col, channel chunk) of the next k-block this group loads
+        // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block this group loads; this lane's channel
+        //      quad of that k-block is g = 8 kb + chunk -> (tap, quad in tap) by multiply-shift division
         int oy[8], ox[8], rowoff[8];
-        int l_ti = 0, l_ky = 0, l_kx = 0, l_kc = 0, cur_ti = -1;
-        auto advance = [&]() {
-            if (++l_kc == KC) {
-                l_kc = 0;
-                if (++l_kx == KW) {
-                    l_kx = 0;
-                    if (++l_ky == KH) { l_ky = 0; ++l_ti; }
-                }
-            }
-        };
-        if (grp) advance();
+        int l_ti = 0, l_kb = grp, cur_ti = -1;
+        while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         auto set_tile = [&](int ti) {
             cur_ti = ti;
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -320,11 +325,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             }
         };
         // ---- load phase: this lane's 8 x 16-byte global loads of one k-block (predicated, branch-free)
-        auto load_kb = [&](F4(&v)[8], uint32_t &mask) {
+        auto load_kb = [&](F4(&v)[8], uint32_t &mask, int &c_out) {
             if (l_ti != cur_ti) set_tile(l_ti);
-            const int dy = l_ky * dil, dx = l_kx * dil;
-            const int c = l_kc * 32 + c0;          // first channel of this lane's 16-byte unit
-            const bool cok = c < Cin;
+            const uint32_t g = (uint32_t)(l_kb * 8 + chunk);
+            const uint32_t tap = fdiv(g, p.fd_cq);
+            const uint32_t ky = fdiv(tap, p.fd_kw);
+            const int kx = (int)(tap - ky * (uint32_t)KW);
+            const int dy = (int)ky * dil, dx = kx * dil;
+            const bool cok = (int)tap < taps;      // quads past the last tap pad the final k-block
+            const int c = cok ? (int)(g - tap * (uint32_t)p.CQ) * 4 : 0;   // first channel of this lane's 16-byte unit
+            c_out = c;
             const int tapoff = UP ? c : (dy * Ws + dx) * xs + c;
             uint32_t mk = 0;
 #pragma unroll
@@ -349,26 +359,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 }
             }
             mask = mk;
-            advance();
-            advance();
+            l_kb += 2;
+            while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         };
         // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
         //      hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is
         //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
         int s_s = grp;                             // stage of this group's next store (S >= 2)
         uint32_t s_ph = 0;
-        int s_kc = grp;
-        while (s_kc >= KC) s_kc -= KC;
-        auto store_kb = [&](F4(&v)[8], uint32_t mask) {
-            const int c = s_kc * 32 + c0;
+        auto store_kb = [&](F4(&v)[8], uint32_t mask, const int c) {
             const uint32_t a_hi = base + (uint32_t)s_s * stage_bytes + roff0;
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
             const uint32_t bar_full = full_a(s_s);
             mbar_wait(empty(s_s), s_ph ^ 1);
             s_s += 2;
             if (s_s >= S) { s_s -= S; s_ph ^= 1; }
-            s_kc += 2;
-            while (s_kc >= KC) s_kc -= KC;
             float sc[4], sh[4];
             if (AFF) {
                 const float4 a4 = *reinterpret_cast<const float4 *>(s_scale + c);
@@ -413,15 +418,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         {
             F4 va[8], vb[8];
             uint32_t ma = 0, mb = 0;
+            int ca = 0, cb = 0;
             const int mine = (total_kb - grp + 1) >> 1;   // k-blocks of this group
             int issued = 0;
-            if (issued < mine) { load_kb(va, ma); ++issued; }
+            if (issued < mine) { load_kb(va, ma, ca); ++issued; }
             for (int done = 0; done < mine; done += 2) {
-                if (issued < mine) { load_kb(vb, mb); ++issued; }
-                store_kb(va, ma);
+                if (issued < mine) { load_kb(vb, mb, cb); ++issued; }
+                store_kb(va, ma, ca);
                 if (done + 1 < mine) {
-                    if (issued < mine) { load_kb(va, ma); ++issued; }
-                    store_kb(vb, mb);
+                    if (issued < mine) { load_kb(va, ma, ca); ++issued; }
+                    store_kb(vb, mb, cb);
                 }
             }
         }
@@ -454,30 +460,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 } else {
                     tmem_ld_wait();
                 }
+                float ov[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float a = __uint_as_float(r[e]);
+                    if (p.act == 1) a = a > 0.f ? a : expm1f(a);
+                    else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
+                    ov[e] = a;
+                }
                 if (m < p.M) {
                     const int cbase = nt * n_tile + cc;          // absolute output channel
 #pragma unroll
                     for (int e4 = 0; e4 < 16; e4 += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float a = __uint_as_float(r[e4 + e]);
-                            if (p.act == 1) a = a > 0.f ? a : expm1f(a);
-                            else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
-                            o[e] = a;
-                        }
                         if (ovec && cbase + e4 + 3 < p.Cout) {
-                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(ov[e4], ov[e4 + 1], ov[e4 + 2], ov[e4 + 3]);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = o[e];
+                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = ov[e4 + e];
                         }
+                    }
+                }
+                if (p.stat_sum) {
+                    // BatchNorm batch statistics of the tensor being produced (bts_bn_stats fused into its producer):
+                    // column sums over the warp's 32 rows by a transposing butterfly (16 shuffles per quantity instead
+                    // of 80), then shared-memory partials per CTA; flushed once per CTA with fp64 atomics below.
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float a = m < p.M ? ov[e] : 0.f;
+                        s1[e] = a;
+                        s2[e] = a * a;
+                    }
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1) {            // lane mask 16, 8, 4, 2 <-> keep 8, 4, 2, 1 columns
+                        const bool upper = (lane & (2 * w)) != 0;
+#pragma unroll
+                        for (int j = 0; j < w; ++j) {
+                            const float k1 = upper ? s1[w + j] : s1[j], d1 = upper ? s1[j] : s1[w + j];
+                            const float k2 = upper ? s2[w + j] : s2[j], d2 = upper ? s2[j] : s2[w + j];
+                            s1[j] = k1 + __shfl_xor_sync(0xffffffffu, d1, 2 * w);
+                            s2[j] = k2 + __shfl_xor_sync(0xffffffffu, d2, 2 * w);
+                        }
+                    }
+                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                    const int col = cc + (lane >> 1);             // lane bits 4..1 = column within the 16-column group
+                    if ((lane & 1) == 0 && col < p.Cout) {
+                        atomicAdd(&s_stat[col], s1[0]);
+                        atomicAdd(&s_stat[MAX_N + col], s2[0]);
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));        // this thread is done reading the accumulator
+        }
+        if (p.stat_sum) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+            for (int c = (int)threadIdx.x - (NUM_THREADS - EPI_THREADS); c < p.Cout; c += EPI_THREADS) {
+                atomicAdd(p.stat_sum + c, (double)s_stat[c]);
+                atomicAdd(p.stat_sumsq + c, (double)s_stat[MAX_N + c]);
+            }
         }
     }
     tc_fence_before();
@@ -502,8 +545,9 @@ extern "C" int bts_conv_n_tile(int Cout) {
 extern "C" long long bts_conv_packed_floats(int n_rows, int k_channels, int KH, int KW) {
     const int n_tile = bts_conv_n_tile(n_rows);
     const int n_tiles = (n_rows + n_tile - 1) / n_tile;
-    const int KC = (k_channels + 31) / 32;
-    return (long long)n_tiles * KH * KW * KC * 2 * n_tile * 32;
+    const int CQ = (k_channels + 3) / 4;
+    const int KB = (KH * KW * CQ + 7) / 8;
+    return (long long)n_tiles * KB * 2 * n_tile * 32;
 }
 
 extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
@@ -523,10 +567,11 @@ extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s
     return 0;
 }
 
-extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
-                            int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
-                            const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
-                            long long out_pixel_stride, int act, int precision, void *stream) {
+static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                         int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                         const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
+                         long long out_pixel_stride, int act, int precision, double *stat_sum, double *stat_sumsq,
+                         void *stream) {
     if (!x || !wpack || !out || B < 0 || Hs < 1 || Ws < 1 || Cin < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 ||
         pad < 0 || dil < 1)
         return BTS_EINVAL;
@@ -544,13 +589,19 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     p.n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
     p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu ? 1 : 0;
     p.out = out; p.os = out_pixel_stride; p.act = act; p.precision = precision;
+    p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+    if ((stat_sum == nullptr) != (stat_sumsq == nullptr)) return BTS_EINVAL;
+    if (stat_sum && p.n_tiles != 1) return BTS_EINVAL;           // epilogue statistics: single N tile (Cout <= 256)
     const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
     p.Hout = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
     p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     if (p.Hout < 1 || p.Wout < 1) return BTS_EINVAL;
     p.M = (long long)B * p.Hout * p.Wout;
     p.KC = (Cin + 31) / 32;
-    p.KB = KH * KW * p.KC;
+    p.CQ = (Cin + 3) / 4;
+    p.KB = (KH * KW * p.CQ + 7) / 8;
+    p.fd_cq = make_fastdiv((uint32_t)p.CQ);
+    p.fd_kw = make_fastdiv((uint32_t)KW);
     p.vec_ok = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
     const long long m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     if (m_tiles * p.n_tiles * (long long)p.KB > 0x7fffffffLL || p.M + BLOCK_M >= 0x7fffffffLL) return BTS_EINVAL;
@@ -563,10 +614,11 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
     // shared-memory plan: stage = A hi/lo (2 x 16 KB) + B hi/lo (2 x n_tile x 128 B); as many stages as fit
     p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.n_tile * 128;
     const int pre_bytes = pre >= 2 ? p.KC * 32 * 8 : 0;
-    p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes) / p.stage_bytes;
+    const int stat_bytes = stat_sum ? STAT_BYTES : 0;
+    p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes - stat_bytes) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return BTS_EINVAL;
-    const int smem = p.stages * p.stage_bytes + pre_bytes + BAR_BYTES + 1024;
+    const int smem = p.stages * p.stage_bytes + pre_bytes + BAR_BYTES + stat_bytes + 1024;
     const int sms = bts_num_sms();
     dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
@@ -597,4 +649,22 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
 #undef BTS_LAUNCH
     BTS_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                            int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                            const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
+                            long long out_pixel_stride, int act, int precision, void *stream) {
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2, Cin, KH, KW, stride, pad, dil, wpack, Cout, pre_scale,
+                         pre_shift, pre_relu, out, out_pixel_stride, act, precision, nullptr, nullptr, stream);
+}
+
+extern "C" int bts_conv_fwd_stats(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+                                  int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                                  const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
+                                  long long out_pixel_stride, int act, int precision, double *stat_sum,
+                                  double *stat_sumsq, void *stream) {
+    if (!stat_sum || !stat_sumsq) return BTS_EINVAL;
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2, Cin, KH, KW, stride, pad, dil, wpack, Cout, pre_scale,
+                         pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq, stream);
 }

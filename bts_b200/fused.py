@@ -24,6 +24,7 @@ from . import _lib, conv
 from .ops import _ptr, _stream
 
 FUSE = os.environ.get("BTS_B200_FUSE", "1") == "1"
+EPI_STATS = os.environ.get("BTS_B200_EPI_STATS", "1") == "1"   # BatchNorm batch statistics reduced in the conv epilogue
 
 
 def _view(t):
@@ -104,11 +105,16 @@ class _DenseBlockFn(torch.autograd.Function):
         for li, layer in enumerate(layers):
             w1, w2 = params[6 * li + 2], params[6 * li + 5]
             st1 = bn_finalize(sums[:, :C] if training else None, n, layer.norm1, training)
-            b = conv.conv2d_tc(slab[:, :C], w1, 1, 0, 1, pre_scale=st1[0], pre_shift=st1[1], pre_relu=True)
-            st2 = bn_finalize(bn_stats(b) if training else None, n, layer.norm2, training)
-            conv.conv2d_tc(b, w2, 1, 1, 1, pre_scale=st2[0], pre_shift=st2[1], pre_relu=True, out=slab[:, C:C + growth])
-            if training and li + 1 < len(layers):
-                sums[:, C:C + growth] = bn_stats(slab[:, C:C + growth])
+            epi = training and EPI_STATS and w1.shape[0] <= 256 and growth <= 256
+            sb = torch.zeros((2, w1.shape[0]), device=x.device, dtype=torch.float64) if epi else None
+            b = conv.conv2d_tc(slab[:, :C], w1, 1, 0, 1, pre_scale=st1[0], pre_shift=st1[1], pre_relu=True, stats=sb)
+            st2 = bn_finalize((sb if epi else bn_stats(b)) if training else None, n, layer.norm2, training)
+            more = training and li + 1 < len(layers)
+            sn = torch.zeros((2, growth), device=x.device, dtype=torch.float64) if (epi and more) else None
+            conv.conv2d_tc(b, w2, 1, 1, 1, pre_scale=st2[0], pre_shift=st2[1], pre_relu=True, out=slab[:, C:C + growth],
+                           stats=sn)
+            if more:
+                sums[:, C:C + growth] = sn if sn is not None else bn_stats(slab[:, C:C + growth])
             saved_b.append(b)
             saved_st += [st1, st2]
             C += growth

@@ -188,3 +188,21 @@ def test_pointwise_wgrad_cuda_core_kernel(Cin, Cout, monkeypatch):
     gw = conv.wgrad_tc(slab[:, 4:4 + Cin], gy.cuda(), (Cout, Cin, 1, 1), (Cin, 1, 1, 1), 1, 0, 1)
     ref2 = torch.einsum("bohw,bihw->oi", gy.double(), slab[:, 4:4 + Cin].cpu().double()).reshape(Cout, Cin, 1, 1)
     assert (gw.cpu().double() - ref2).abs().max() / ref2.abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,k,H,W,act", [(40, 48, 3, 13, 21, None), (96, 192, 1, 9, 14, None), (36, 32, 3, 20, 28, "elu"),
+                                                 (64, 256, 1, 8, 8, None)])
+def test_conv_epilogue_batch_statistics(Cin, Cout, k, H, W, act):
+    """per-channel sum / sum of squares of the conv output reduced in the epilogue (bts_conv_fwd_stats) == a separate pass"""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(3, Cin, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    st = torch.zeros((2, Cout), device="cuda", dtype=torch.float64)
+    y = conv.conv2d_tc(x, w, 1, k // 2, 1, act=act, stats=st)
+    y0 = conv.conv2d_tc(x, w, 1, k // 2, 1, act=act)
+    assert torch.equal(y, y0)
+    yd = y.double()
+    s1, s2 = yd.sum((0, 2, 3)), (yd * yd).sum((0, 2, 3))
+    assert (st[0] - s1).abs().max() <= 1e-5 * s2.sqrt().max()
+    assert ((st[1] - s2).abs() / s2).max() < 1e-5
