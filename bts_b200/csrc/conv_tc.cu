@@ -460,24 +460,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 } else {
                     tmem_ld_wait();
                 }
-                float ov[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float a = __uint_as_float(r[e]);
-                    if (p.act == 1) a = a > 0.f ? a : expm1f(a);
-                    else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
-                    ov[e] = a;
-                }
                 if (m < p.M) {
                     const int cbase = nt * n_tile + cc;          // absolute output channel
 #pragma unroll
                     for (int e4 = 0; e4 < 16; e4 += 4) {
+                        float o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float a = __uint_as_float(r[e4 + e]);
+                            if (p.act == 1) a = a > 0.f ? a : expm1f(a);
+                            else if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
+                            o[e] = a;
+                        }
                         if (ovec && cbase + e4 + 3 < p.Cout) {
-                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(ov[e4], ov[e4 + 1], ov[e4 + 2], ov[e4 + 3]);
+                            *reinterpret_cast<float4 *>(orow + cc + e4) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = ov[e4 + e];
+                                if (cbase + e4 + e < p.Cout) orow[cc + e4 + e] = o[e];
                         }
                     }
                 }
@@ -485,10 +485,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     // BatchNorm batch statistics of the tensor being produced (bts_bn_stats fused into its producer):
                     // column sums over the warp's 32 rows by a transposing butterfly (16 shuffles per quantity instead
                     // of 80), then shared-memory partials per CTA; flushed once per CTA with fp64 atomics below.
+                    // (host guarantees act == none here: the statistics are those of the raw conv output)
                     float s1[16], s2[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const float a = m < p.M ? ov[e] : 0.f;
+                        const float a = m < p.M ? __uint_as_float(r[e]) : 0.f;
                         s1[e] = a;
                         s2[e] = a * a;
                     }
@@ -591,7 +592,7 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     p.out = out; p.os = out_pixel_stride; p.act = act; p.precision = precision;
     p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
     if ((stat_sum == nullptr) != (stat_sumsq == nullptr)) return BTS_EINVAL;
-    if (stat_sum && p.n_tiles != 1) return BTS_EINVAL;           // epilogue statistics: single N tile (Cout <= 256)
+    if (stat_sum && (p.n_tiles != 1 || act != 0)) return BTS_EINVAL;   // epilogue statistics: one N tile (Cout <= 256), no activation
     const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
     p.Hout = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
     p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
