@@ -250,7 +250,11 @@ def run_ours(args):
     freeze_like_set_misc(model)
     model.to(dev)
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        # bts_main.py:352 passes find_unused_parameters=True because the ResNet/ResNeXt encoders keep a never-used `fc`
+        # (SURVEY Q11); DenseNet-161 has no unused parameter, so the extra autograd traversal is switched off here.
+        unused = any(k.startswith("encoder.base_model.fc") for k, _ in model.named_parameters())
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=unused,
+                                                          gradient_as_bucket_view=True)
     opt = make_optimizer(model, torch)
     crit = bts.silog_loss(0.85)
     B = B_PER_GPU

@@ -8,6 +8,8 @@
 // one the tensor core accepts for MN-major TF32), UMMA descriptors with a_major = b_major = MN, LBO = chunk stride.
 // grid = (ceil(Cin/128), n_tiles(Cout), taps * splitK); each CTA reduces its pixel range into an fp32 TMEM tile and
 // writes a partial; a second, deterministic kernel sums the splitK partials into the (Cout,Cin,KH,KW)-strided gradient.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -16,8 +18,9 @@ namespace {
 
 constexpr int BLOCK_CI = 128;
 constexpr int BLOCK_KP = 32;                 // pixels per k-block
-constexpr int MAX_N = 128;
-constexpr int STAGES = 3;
+constexpr int MAX_N = 256;                   // output channels per CTA tile (one tcgen05.mma covers up to 256)
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_LIMIT = 232448;
 constexpr int CHUNK_BYTES = BLOCK_KP * 128;  // one 32-channel chunk of a k-block: 4 KB
 constexpr int A_BYTES = 4 * CHUNK_BYTES;     // 16 KB (hi or lo)
 constexpr int NUM_THREADS = 576;               // 2 control warps + 2 producer groups x 8 warps
@@ -35,28 +38,27 @@ struct WgradParams {
     int splitK, kb_per_split, KBp;
     int M;
     int x_vec, dy_vec, precision;
+    int stages, stage_bytes;     // operand ring: [A hi 16K | A lo 16K | dY hi nchunk*4K | dY lo nchunk*4K] per stage
 };
 
-struct Smem {
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * MAX_N * 128;   // 64 KB
-    static constexpr int PRE_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = PRE_OFF + 2 * BLOCK_CI * 4;
-    static constexpr int TOTAL = BAR_OFF + 256;
-};
 
 template <int PRE, bool UP, bool VEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
-    float *s_scale = reinterpret_cast<float *>(sm + Smem::PRE_OFF);
+    const int S = p.stages;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    const uint32_t pre_off = (uint32_t)S * stage_bytes;
+    const uint32_t bar_off = pre_off + 2 * BLOCK_CI * 4;
+    float *s_scale = reinterpret_cast<float *>(sm + pre_off);
     float *s_shift = s_scale + BLOCK_CI;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + Smem::BAR_OFF);
-    const uint32_t bar0 = base + Smem::BAR_OFF;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + bar_off);
+    const uint32_t bar0 = base + bar_off;
     auto full = [&](int s) { return bar0 + 8u * s; };
-    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    const uint32_t accum_full = bar0 + 8u * (2 * STAGES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    auto empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    const uint32_t accum_full = bar0 + 8u * (2 * MAX_STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci_tile = blockIdx.x, nt = blockIdx.y;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
     const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < S; ++s) {
             mbar_init(full(s), 2 * GROUP_THREADS);      // both producer groups (x tile + dY tile) arrive
             mbar_init(empty(s), 1);
         }
@@ -84,9 +86,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         }
     }
     // chunks of the A operand beyond the last live input channel are never produced: zero them once
-    for (int i = threadIdx.x; i < STAGES * 2 * A_BYTES / 16; i += NUM_THREADS) {
+    for (int i = threadIdx.x; i < S * 2 * A_BYTES / 16; i += NUM_THREADS) {
         const int st_ = i / (2 * A_BYTES / 16), r_ = i % (2 * A_BYTES / 16);
-        st_shared_v4(base + st_ * Smem::STAGE_BYTES + r_ * 16, 0.f, 0.f, 0.f, 0.f);
+        st_shared_v4(base + (uint32_t)st_ * stage_bytes + r_ * 16, 0.f, 0.f, 0.f, 0.f);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -102,26 +104,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             const int nchunk_b = (n_tile + 31) >> 5;
             const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
             const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
+            const bool stack = n_tile <= 128;          // wider tiles: three plain products per k-group
+            int s = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nkb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(full(s), ph);
                 tc_fence_after();
-                const uint32_t a_hi = base + s * Smem::STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + (uint32_t)nchunk_b * CHUNK_BYTES;
 #pragma unroll
                 for (int kg = 0; kg < BLOCK_KP / 8; ++kg) {
                     const uint64_t dah = make_desc_mn(a_hi + kg * 1024, CHUNK_BYTES), dal = make_desc_mn(a_lo + kg * 1024, CHUNK_BYTES);
                     const uint64_t dbh = make_desc_mn(b_hi + kg * 1024, CHUNK_BYTES), dbl = make_desc_mn(b_lo + kg * 1024, CHUNK_BYTES);
-                    if (p.precision == 0) {
-                        (void)dbl;
+                    if (p.precision == 0 && stack) {
                         umma_tf32(tmem_base, dah, dbh, idesc2, (it | kg) != 0);   // x_hi * [dY_hi ; dY_lo]
                         umma_tf32(tmem_base, dal, dbh, idesc, 1);                 // x_lo * dY_hi
+                    } else if (p.precision == 0) {
+                        umma_tf32(tmem_base, dal, dbh, idesc, (it | kg) != 0);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1);
                     } else {
                         umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
                     }
                 }
                 umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1; }
             }
             umma_commit(accum_full);
         }
@@ -232,9 +239,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     }
                 }
             };
+            int xs_s = 0;
+            uint32_t xs_ph = 0;
             auto store_x = [&](int it, F4(&v)[NU], uint32_t mask) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int s = xs_s;
+                const uint32_t ph = xs_ph;
+                if (++xs_s == S) { xs_s = 0; xs_ph ^= 1; }
                 if (PRE != 0) {
 #pragma unroll
                     for (int i = 0; i < NU; ++i)
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                         }
                 }
                 mbar_wait(empty(s), ph ^ 1);
-                const uint32_t t_hi = base + s * Smem::STAGE_BYTES;
+                const uint32_t t_hi = base + (uint32_t)s * stage_bytes;
                 split_store(t_hi, t_hi + A_BYTES, v, nlive);
                 fence_proxy_async();
                 mbar_arrive(full(s));
@@ -276,11 +286,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             const int nchunk = (n_tile + 31) >> 5;
             const int cb = nt * n_tile + unit * 4;
             const float *__restrict__ dg = p.dy;
-            auto load_d = [&](int it, F4(&v)[NU]) {
+            // wide tiles (n_tile > 128: 5..8 chunks) are produced in two passes of 4 chunks per k-block; j counts passes
+            const int npass = (nchunk + 3) >> 2;
+            auto load_d = [&](int j, F4(&v)[NU]) {
+                const int it = npass == 2 ? (j >> 1) : j, pass = npass == 2 ? (j & 1) : 0;
                 const int kb = kb0 + it;
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
-                    const int chunk = i;
+                    const int chunk = pass * 4 + i;
                     const int m = kb * BLOCK_KP + r0;
                     const int c = cb + chunk * 32;
                     const bool live = chunk < nchunk && m < p.M && c < p.Cout;
@@ -303,24 +316,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     }
                 }
             };
-            auto store_d = [&](int it, F4(&v)[NU]) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(empty(s), ph ^ 1);
-                const uint32_t t_hi = base + s * Smem::STAGE_BYTES + 2 * A_BYTES;
-                split_store(t_hi, t_hi + (uint32_t)nchunk * CHUNK_BYTES, v, nchunk);
-                fence_proxy_async();
-                mbar_arrive(full(s));
+            int ds_s = 0;
+            uint32_t ds_ph = 0;
+            auto store_d = [&](int j, F4(&v)[NU]) {
+                const int pass = npass == 2 ? (j & 1) : 0;
+                const int s = ds_s;
+                if (pass == 0) mbar_wait(empty(s), ds_ph ^ 1);
+                const uint32_t t_hi = base + (uint32_t)s * stage_bytes + 2 * A_BYTES + (uint32_t)pass * 4u * CHUNK_BYTES;
+                split_store(t_hi, t_hi + (uint32_t)nchunk * CHUNK_BYTES, v, nchunk - pass * 4);
+                if (pass == npass - 1) {
+                    fence_proxy_async();
+                    mbar_arrive(full(s));
+                    if (++ds_s == S) { ds_s = 0; ds_ph ^= 1; }
+                }
             };
             F4 va[NU], vb[NU];
+            const int nj = nkb * npass;
             int it = 0;
-            if (it < nkb) load_d(it, va);
-            for (; it < nkb; it += 2) {
-                const bool more = it + 1 < nkb;
+            if (it < nj) load_d(it, va);
+            for (; it < nj; it += 2) {
+                const bool more = it + 1 < nj;
                 if (more) load_d(it + 1, vb);
                 store_d(it, va);
                 if (more) {
-                    if (it + 2 < nkb) load_d(it + 2, va);
+                    if (it + 2 < nj) load_d(it + 2, va);
                     store_d(it + 1, vb);
                 }
             }
@@ -342,7 +361,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         for (int cc = 0; cc < half; cc += 8) {
             uint32_t r[8];
             tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cc), r);
-            if (p.precision == 0) {
+            if (p.precision == 0 && n_tile <= 128) {
                 uint32_t r2[8];
                 tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(lo_col + col0 + cc), r2);
                 tmem_ld_wait();
@@ -395,9 +414,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 
 // N tile of the wgrad kernels (their shared-memory plan holds <= 128 output channels per CTA)
 static int wgrad_n_tile(int Cout) {
+    static int cap = 0;
+    if (!cap) {
+        const char *e = getenv("BTS_B200_WGRAD_WIDE");        // 0: 128-wide tiles (hi/lo stacked), default: up to 256
+        cap = (e && e[0] == '0') ? 128 : MAX_N;
+    }
     int n = (Cout + 15) / 16 * 16;
-    if (n > MAX_N) {
-        const int tiles = (n + MAX_N - 1) / MAX_N;
+    if (n > cap) {
+        const int tiles = (n + cap - 1) / cap;
         n = ((Cout + tiles - 1) / tiles + 15) / 16 * 16;
     }
     return n;
@@ -488,6 +512,14 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
         BTS_LAUNCH_CHECK();
         return 0;
     }
+    {
+        const int nchunk = (p.n_tile + 31) / 32;
+        p.stage_bytes = 2 * A_BYTES + 2 * nchunk * CHUNK_BYTES;
+        p.stages = (SMEM_LIMIT - 1024 - 2 * BLOCK_CI * 4 - 256) / p.stage_bytes;
+        if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+        if (p.stages < 2) return BTS_EINVAL;
+    }
+    const int smem = p.stages * p.stage_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
     dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.n_tile - 1) / p.n_tile, taps * splitK);
     if (grid.z > 65535) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -499,11 +531,11 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
         static bool attr_set = false;                                                                               \
         if (!attr_set) {                                                                                            \
             err = cudaFuncSetAttribute(wgrad_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                       Smem::TOTAL + 1024);                                                         \
+                                       SMEM_LIMIT);                                                                 \
             if (err != cudaSuccess) return (int)err;                                                                \
             attr_set = true;                                                                                        \
         }                                                                                                           \
-        wgrad_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, Smem::TOTAL + 1024, st>>>(p);                            \
+        wgrad_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, smem, st>>>(p);                                          \
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                                                     \
     do {                                                                                         \
