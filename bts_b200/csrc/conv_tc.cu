@@ -446,21 +446,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
             const bool stack = n_tile <= 128 && p.precision == 0;   // columns [n_tile, 2 n_tile) hold A_hi * B_lo
-            // TMEM -> registers is software-pipelined: the tcgen05.ld of the next 16 columns is in flight while the current
-            // ones are converted and stored (the four epilogue warps are the critical path of the short-K, wide-N layers:
-            // the DenseNet 1x1 convs and their dgrads).
-            auto issue = [&](int cc, uint32_t(&r)[16], uint32_t(&r2)[16]) {
+            for (int cc = 0; cc < n_tile; cc += 16) {
+                uint32_t r[16];
                 tmem_ld8(t_addr + (uint32_t)cc, reinterpret_cast<uint32_t(&)[8]>(r[0]));
                 tmem_ld8(t_addr + (uint32_t)cc + 8, reinterpret_cast<uint32_t(&)[8]>(r[8]));
                 if (stack) {
+                    uint32_t r2[16];
                     tmem_ld8(t_addr + (uint32_t)(n_tile + cc), reinterpret_cast<uint32_t(&)[8]>(r2[0]));
                     tmem_ld8(t_addr + (uint32_t)(n_tile + cc) + 8, reinterpret_cast<uint32_t(&)[8]>(r2[8]));
-                }
-            };
-            auto process = [&](int cc, uint32_t(&r)[16], uint32_t(&r2)[16]) {
-                if (stack) {
+                    tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+                } else {
+                    tmem_ld_wait();
                 }
                 if (m < p.M) {
                     const int cbase = nt * n_tile + cc;          // absolute output channel
@@ -513,18 +511,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                         atomicAdd(&s_stat[col], s1[0]);
                         atomicAdd(&s_stat[MAX_N + col], s2[0]);
                     }
-                }
-            };
-            uint32_t ra[16], ra2[16], rb[16], rb2[16];
-            issue(0, ra, ra2);
-            for (int cc = 0; cc < n_tile; cc += 32) {
-                tmem_ld_wait();
-                if (cc + 16 < n_tile) issue(cc + 16, rb, rb2);
-                process(cc, ra, ra2);
-                if (cc + 16 < n_tile) {
-                    tmem_ld_wait();
-                    if (cc + 32 < n_tile) issue(cc + 32, ra, ra2);
-                    process(cc + 16, rb, rb2);
                 }
             }
             tc_fence_before();
