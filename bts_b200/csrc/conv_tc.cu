@@ -10,12 +10,14 @@
 //              (upconv, bts.py:77) which is folded into the address map -- the 4x tensor is never materialised.
 //       act  = none | ELU | sigmoid, fused in the epilogue.
 //
-// GEMM view: M = B*Hout*Wout pixels (128 per CTA tile = the 128 TMEM lanes), N = Cout (<=128 per tile),
-// K = taps * Cin in blocks of 32 fp32 (one 128-byte swizzled row per pixel).
+// GEMM view: M = B*Hout*Wout pixels (128 per CTA tile = the 128 TMEM lanes), N = Cout (<=256 per tile),
+// K = the dense sequence of 16-byte channel quads, tap-major, in blocks of 32 fp32 (one 128-byte swizzled row per pixel).
 // Precision: fp32 operands are split x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) and the tile
 // accumulates  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  with kind::tf32 MMAs into fp32 TMEM accumulators (error
-// ~2^-21 per product: fp32-grade).  Single-pass TF32 is available as an explicitly
-// labelled fast mode (precision=1) and is NOT used for parity.
+// ~2^-21 per product: fp32-grade).  For N <= 128, A_hi*[B_hi;B_lo] is
+// ONE instruction of width 2N (the epilogue adds the two column blocks) and A_lo*B_hi the second -- a tcgen05.mma of
+// this shape costs ~120 cycles whatever N is, so the MMA count, not the FLOP count, sets the speed (see the MMA issuer).
+// Single-pass TF32 is available as an explicitly labelled fast mode (precision=1) and is NOT used for parity.
 //
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ... with the smem stage
 // ring, the two TMEM accumulators and all warp roles running continuously across tile boundaries (the MMA of tile
@@ -28,8 +30,9 @@
 //   warps 2..9  : two producer groups (alternating k-blocks): coalesced 128-bit global loads of the activation
 //                 tile (8 lanes cover one pixel's 128 B), pre-op + hi/lo split in registers, swizzled 128-bit
 //                 shared stores of both halves, fence.proxy.async, mbarrier arrive;
-//   warps 10..13: epilogue: wait for the tile's accumulator, tcgen05.ld of the 128 rows, activation, vectorised
-//                 NHWC stores, then hand the TMEM accumulator back to the MMA warp.
+//   warps 10..13: epilogue: wait for the tile's accumulator, tcgen05.ld of the 128 rows, hi/lo block add, activation,
+//                 vectorised NHWC stores, optional BatchNorm batch statistics of the output, then hand the TMEM
+//                 accumulator back to the MMA warp.
 #include <cstdio>
 #include <cstdlib>
 

@@ -8,6 +8,9 @@
 // one the tensor core accepts for MN-major TF32), UMMA descriptors with a_major = b_major = MN, LBO = chunk stride.
 // grid = (ceil(Cin/128), n_tiles(Cout), taps * splitK); each CTA reduces its pixel range into an fp32 TMEM tile and
 // writes a partial; a second, deterministic kernel sums the splitK partials into the (Cout,Cin,KH,KW)-strided gradient.
+// n_tile <= 128: two tcgen05.mma per k-group (x_hi^T*[dY_hi;dY_lo] as one instruction of width 32*nchunk + n_tile, then
+// x_lo^T*dY_hi); 128 < n_tile <= 256: one tile, three plain products, the dY tile produced in two passes of 4 chunks.
+// 576 threads: MMA issuer warp + 2 producer groups of 8 warps (x tile / dY tile), 2-4 operand stages as smem allows.
 #include <cstdlib>
 
 #include "tc_common.cuh"
