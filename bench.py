@@ -224,7 +224,34 @@ def lpg_roofline(torch, dev, pk):
             "algorithmic_bytes": (4.0 * 128 * 1024 * 1024) * ((1 + 4.0 / 64) + (1 + 8.0 / 64)), "sweep": out}
 
 
+class StdoutToStderr:
+    """While active, file descriptor 1 points at stderr: library chatter (e.g. the "NCCL version ..." banner NCCL prints on
+    stdout at communicator creation) cannot precede the ONE JSON line this script owes its caller on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_ours(args):
+    with StdoutToStderr():
+        res, rank, dist = _run_ours(args)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    if dist is not None:
+        with StdoutToStderr():
+            dist.destroy_process_group()
+
+
+def _run_ours(args):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -337,16 +364,15 @@ def run_ours(args):
                 res["roofline"] = lpg_roofline(torch, dev, pk)
             if not args.no_cpu:
                 res["cpu_baseline"] = cpu_reference_steps(3, 1)
-        print(json.dumps(res), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return res, rank, (dist if world > 1 else None)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_steps(args.steps, args.warmup)
+    with StdoutToStderr():
+        r = cpu_reference_steps(args.steps, args.warmup)
     res = {"impl": "reference", "metric": "training images/sec (352x704, DenseNet-161)", "value": r["value"],
            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
