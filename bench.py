@@ -10,7 +10,8 @@ parameter groups and poly LR of bts_main.py:371-373,456-460.  A "step" = zero_gr
 optimizer step over one batch.  `value` is timed with inputs resident in HBM; `e2e` repeats the measurement with
 the batch starting in pinned host memory (H2D inside the timed region) and the loss read back (D2H) every step.
 `roofline` is the LPG plane-to-depth kernel pair (the kernel BASELINE.json's metric names), timed live with CUDA
-events on the launching stream; `roofline_step` relates the whole step to the conv-FLOP roof.
+events on the launching stream; `roofline_conv` is one layer of the step's dominant kernel (the tcgen05 conv engine)
+timed the same way against the 3xTF32 tensor roof; `roofline_step` relates the whole step to the conv-FLOP roof.
 """
 import argparse
 import json
@@ -224,6 +225,43 @@ def lpg_roofline(torch, dev, pk):
             "algorithmic_bytes": (4.0 * 128 * 1024 * 1024) * ((1 + 4.0 / 64) + (1 + 8.0 / 64)), "sweep": out}
 
 
+def conv_roofline(torch, dev, pk):
+    """The dominant kernel of the step by time is the conv engine (conv_tc_kernel: every forward and dgrad).  One of its
+    layers, timed live: daspp_conv 896->128 3x3 at 44x88, batch 16 (input 222 MB > 126 MB L2, so consecutive launches
+    cannot be served from L2), 20 back-to-back launches between two CUDA events on the launching stream.
+    achieved = nominal dense FLOPs (2*B*H*W*Cout*Cin*9) / average launch time; peak = the parity-mode (3xTF32) tensor
+    roof derived from the measured bf16 throughput: bf16 / 2 (tf32) / 3 (three products)."""
+    from bts_b200 import conv
+    B, Cin, H, W, Cout, k = 16, 896, 44, 88, 128, 3
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(B, Cin, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(Cout, Cin, k, k, device=dev, generator=g) / (Cin * k * k) ** 0.5
+    packed = conv.pack_weights(w)
+    run = lambda: conv.conv2d_tc(x, w, 1, 1, 1, packed=packed)
+    reps = 20
+    run()
+    run()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        run()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * B * H * W * Cout * Cin * k * k
+    a = flops / ms / 1e9
+    peak = pk["bf16_tflops"] / 6.0
+    del x, w, packed
+    torch.cuda.empty_cache()
+    return {"bound": "tensor", "kernel": "conv_tc_kernel, daspp_conv 896->128 3x3 @16x44x88 (3xTF32, N-stacked hi/lo MMAs), "
+                                         "%d back-to-back launches" % reps,
+            "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak, "ms_per_launch": ms,
+            "peak_source": "bf16 sustained / 2 / 3; " + pk["source"], "traffic": None,
+            "algorithmic_flops": flops}
+
+
 class StdoutToStderr:
     """While active, file descriptor 1 points at stderr: library chatter (e.g. the "NCCL version ..." banner NCCL prints on
     stdout at communicator creation) cannot precede the ONE JSON line this script owes its caller on stdout."""
@@ -362,6 +400,10 @@ def _run_ours(args):
                 del model, opt
                 torch.cuda.empty_cache()
                 res["roofline"] = lpg_roofline(torch, dev, pk)
+                try:
+                    res["roofline_conv"] = conv_roofline(torch, dev, pk)
+                except Exception as e:             # an evidence leg must never cost the bench line
+                    res["roofline_conv"] = {"error": "%s: %s" % (type(e).__name__, e)}
             if not args.no_cpu:
                 res["cpu_baseline"] = cpu_reference_steps(3, 1)
     return res, rank, (dist if world > 1 else None)
