@@ -1,17 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- training images/sec of the BTS hot path on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N>1, one rank per GPU)
-    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W [--config K16|N4|R8|T1|LPG]    # our arm (torchrun launches N>1)
+    python bench.py --impl reference --gpus N --steps K ...                      # reference arm: the reference on host cores
 
-Workload (config K16, BASELINE.json configs[1]): DenseNet-161 encoder, 352x704 synthetic RGB->depth, batch 16
-PER GPU (weak scaling), train mode (batch-stat BN), silog loss (lambda .85), backward, AdamW step with the two
-parameter groups and poly LR of bts_main.py:371-373,456-460.  A "step" = zero_grad + forward + loss + backward +
-optimizer step over one batch.  `value` is timed with inputs resident in HBM; `e2e` repeats the measurement with
-the batch starting in pinned host memory (H2D inside the timed region) and the loss read back (D2H) every step.
-`roofline` is the LPG plane-to-depth kernel pair (the kernel BASELINE.json's metric names), timed live with CUDA
-events on the launching stream; `roofline_conv` is one layer of the step's dominant kernel (the tcgen05 conv engine)
-timed the same way against the 3xTF32 tensor roof; `roofline_step` relates the whole step to the conv-FLOP roof.
+Default workload K16 (BASELINE.json configs[1], the config the metric is quoted on): DenseNet-161 encoder, 352x704
+synthetic RGB->depth, batch 16 PER GPU (weak scaling), train mode (batch-stat BN), silog loss (lambda .85), backward,
+AdamW step with the two parameter groups and poly LR of bts_main.py:371-373,456-460.  A "step" = zero_grad + forward +
+loss + backward + optimizer step over one batch.  Other configs (BASELINE.json configs[0,2,3,4]) via --config:
+N4 = DN-161 416x544 NYU-shape B=4/GPU, R8 = ResNeXt-101 352x704 B=8/GPU, T1 = DN-121 416x544 B=1 eval forward,
+LPG = the LPG-only microbench (r = 8/4/2, H=W = 256..1024, HBM regime and B=16 regime).
+
+Keys:
+  value          K timed steps, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e            same metric with the batch starting in pinned host memory (H2D inside the timed region) and the loss read
+                 back (D2H) every step
+  roofline       the DOMINANT kernel of the step (conv_tc_kernel: every conv forward and dgrad): nominal FLOPs of all of
+                 its launches in one step / the sum of their CUDA-event durations inside a real step (FLOP-weighted), against
+                 the parity-mode tensor roof = measured TF32 GEMM peak (sustained: the kernel is timed inside a long step) / 3
+  roofline_wgrad same for the wgrad kernels;  roofline_lpg: the LPG fwd+bwd pair against the measured HBM peak (burst:
+                 timed in isolation);  roofline_step: whole step, nominal conv FLOPs / step time
+  peaks_live     TF32 GEMM peak measured by this run the way MEASURED_PEAKS.json was made for bf16 (cuBLAS 8192^3)
+  gpu_baseline   the reference model (unmodified pytorch/bts.py when oracle/_ref travelled, else the oracle port) under
+                 stock torch-eager + cuDNN on the same GPU, fp32 (TF32 off) and with PyTorch's default cudnn TF32
+  cpu_baseline   the reference on the box's host cores (bounded sample)
 """
 import argparse
 import json
@@ -26,30 +38,53 @@ import types
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, B_PER_GPU = 352, 704, 16
-FOCAL = 721.5377
-MAX_DEPTH = 80.0
-GFLOP_PER_IMG_TRAIN = 588.0      # nominal conv FLOPs, fwd+dgrad+wgrad, DN-161 @352x704
+# name: encoder, H, W, batch per GPU, dataset, max_depth, focal, valid fraction of gt, mask threshold, train,
+#       nominal conv GFLOP per image (train = fwd+dgrad+wgrad; T1 = forward only)
+CONFIGS = {
+    "K16": dict(encoder="densenet161_bts", H=352, W=704, B=16, dataset="kitti", max_depth=80.0, focal=721.5377,
+                valid=0.2, thr=1.0, train=True, gflop=588.0,
+                workload="K16: DenseNet-161 encoder, 352x704 KITTI-shape synthetic, batch 16/GPU, train step "
+                         "(fwd + silog + bwd + AdamW), random-init weights",
+                metric="training images/sec (352x704, DenseNet-161)"),
+    "N4": dict(encoder="densenet161_bts", H=416, W=544, B=4, dataset="nyu", max_depth=10.0, focal=518.8579,
+               valid=0.95, thr=0.1, train=True, gflop=537.0,
+               workload="N4: DenseNet-161 encoder, 416x544 NYU-shape synthetic, batch 4/GPU, train step "
+                        "(fwd + silog + bwd + AdamW), random-init weights",
+               metric="training images/sec (416x544, DenseNet-161)"),
+    "R8": dict(encoder="resnext101_bts", H=352, W=704, B=8, dataset="kitti", max_depth=80.0, focal=721.5377,
+               valid=0.2, thr=1.0, train=True, gflop=893.0,
+               workload="R8: ResNeXt-101 (32x8d) encoder, 352x704 KITTI-shape synthetic, batch 8/GPU, train step "
+                        "(fwd + silog + bwd + AdamW), random-init weights",
+               metric="training images/sec (352x704, ResNeXt-101)"),
+    "T1": dict(encoder="densenet121_bts", H=416, W=544, B=1, dataset="nyu", max_depth=10.0, focal=518.8579,
+               valid=0.95, thr=0.1, train=False, gflop=119.5,
+               workload="T1: DenseNet-121 encoder, single 416x544 frame, eval-mode forward only (bts_test.py shape), "
+                        "random-init weights",
+               metric="inference images/sec (416x544, DenseNet-121, batch 1)"),
+}
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                 "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
 
 
-def synth_batch(B, seed, dev="cpu", pin=False):
-    """SURVEY 8d synthetic inputs: image randn, focal 721.5377 (float64 like the DataLoader collate), KITTI-like
-    sparse depth (20% valid, else 0)."""
+def synth_batch(cfg, B, seed, dev="cpu", pin=False):
+    """SURVEY 8d synthetic inputs: image randn, focal (float64 like the DataLoader collate), depth U(0,max_depth) with a
+    Bernoulli validity mask (KITTI-like sparse 20 % / NYU-like dense 95 %, else 0)."""
     import torch
     g = torch.Generator().manual_seed(seed)
+    H, W = cfg["H"], cfg["W"]
     img = torch.randn(B, 3, H, W, generator=g)
-    gt = torch.rand(B, 1, H, W, generator=g) * MAX_DEPTH
-    gt = torch.where(torch.rand(B, 1, H, W, generator=g) < 0.2, gt, torch.zeros_like(gt))
-    focal = torch.full((B,), FOCAL, dtype=torch.float64)
+    gt = torch.rand(B, 1, H, W, generator=g) * cfg["max_depth"]
+    gt = torch.where(torch.rand(B, 1, H, W, generator=g) < cfg["valid"], gt, torch.zeros_like(gt))
+    focal = torch.full((B,), cfg["focal"], dtype=torch.float64)
     if pin:
         return img.pin_memory(), focal.pin_memory(), gt.pin_memory()
     return img.to(dev), focal.to(dev), gt.to(dev)
@@ -63,9 +98,13 @@ def make_optimizer(model, torch):
 
 
 def freeze_like_set_misc(model):
-    """bts_main.py:217-247 default: 'Fixing first conv layer' -> conv0 + every encoder BN affine param frozen."""
+    """bts_main.py:217-247 default ('Fixing first conv layer'): parameters whose name contains one of
+    ['base_model.conv1', '.bn'] (ResNet family) / ['conv0', 'norm'] (DenseNet) are frozen."""
+    names = [n for n, _ in model.encoder.named_parameters()]
+    dense = any("denseblock" in n for n in names)
+    keys = ("conv0", "norm") if dense else ("base_model.conv1", ".bn")
     for name, p in model.encoder.named_parameters():
-        if any(x in name for x in ("conv0", "norm")):
+        if any(x in name for x in keys):
             p.requires_grad = False
 
 
@@ -131,135 +170,270 @@ def usable_cores():
     return n
 
 
-def cpu_reference_steps(steps, warmup, B=2, budget_s=150.0):
-    """The reference algorithm (oracle port of pytorch/bts.py; the Python reference itself does not travel to the
-    GPU box) on all host cores: DN-161, 352x704, one train step per sample batch of B images."""
+# ------------------------------------------------------------------------------------------------ reference legs
+def _reference_model(cfg, torch):
+    """(model, silog criterion, kind, description): the UNMODIFIED reference pytorch/bts.py when it is reachable
+    (oracle/_ref/bts.py, copied there by `make -C oracle`, travels with the working tree; /root/reference in the build
+    container), else the oracle port.  Test/bench infrastructure only."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    p = types.SimpleNamespace(encoder=cfg["encoder"], max_depth=cfg["max_depth"], dataset=cfg["dataset"], bts_size=512)
+    torch.manual_seed(0)
+    if ref_shim.reference_available():
+        R = ref_shim.load_reference()
+        m = R.BtsModel(p)
+        m.decoder.apply(R.weights_init_xavier)
+        crit = R.silog_loss(variance_focus=0.85)
+        return m, (lambda est, gt, mask: crit.forward(est, gt, mask)), "reference", "unmodified pytorch/bts.py (%s)" % ref_shim.REFERENCE_DIR
+    import bts_oracle as O
+    m = O.OracleModel(cfg["encoder"], cfg["max_depth"], cfg["dataset"], 512)
+    return m, (lambda est, gt, mask: O.silog(est, gt, mask, 0.85)), "port", "oracle/bts_oracle.py OracleModel"
+
+
+def cpu_reference_steps(cfg, steps, warmup, B=2, budget_s=150.0):
+    """The reference on all host cores: one train step (or eval forward for T1) per sample batch of B images."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bts_oracle as O
+    import ref_shim
     cores = usable_cores()
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    m = O.OracleModel("densenet161_bts", MAX_DEPTH, "kitti", 512)
-    m.train()
-    opt = torch.optim.AdamW([{"params": m.encoder.parameters(), "weight_decay": 1e-2},
-                             {"params": m.decoder.parameters(), "weight_decay": 0}], lr=1e-4, eps=1e-3)
-    img, focal, gt = synth_batch(B, 1)
-    times = []
-    t_start = time.perf_counter()
-    for i in range(warmup + steps):
-        if times and time.perf_counter() - t_start > budget_s:
-            break                                  # bounded sample: keep the bench within minutes on slow hosts
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        out = m(img, focal)
-        loss = O.silog(out[4], gt, gt > 1.0, 0.85)
-        loss.backward()
-        opt.step()
-        float(loss.detach())
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    with ref_shim.cuda_is_identity():          # the reference's LPG calls .cuda() inside forward (bts.py:140,143)
+        m, crit, kind, what = _reference_model(cfg, torch)
+        train = cfg["train"]
+        if not train:
+            B = 1
+        m.train() if train else m.eval()
+        opt = make_optimizer(m, torch) if train else None
+        img, focal, gt = synth_batch(cfg, B, 1)
+        times = []
+        t_start = time.perf_counter()
+        for i in range(warmup + steps):
+            if times and time.perf_counter() - t_start > budget_s:
+                break                                  # bounded sample: keep the bench within minutes on slow hosts
+            t0 = time.perf_counter()
+            if train:
+                opt.zero_grad()
+                out = m(img, focal)
+                loss = crit(out[4], gt, gt > cfg["thr"])
+                loss.backward()
+                opt.step()
+                float(loss.detach())
+            else:
+                with torch.no_grad():
+                    out = m(img, focal)
+                float(out[4].sum())
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": B * len(times) / total, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "oracle/bts_oracle.py OracleModel (torch CPU fp32, %d threads), DN-161 352x704, B=%d train step "
-                      "(fwd+silog+bwd+AdamW), %d timed steps after %d warm-up" % (cores, B, len(times), warmup),
+    return {"value": B * len(times) / total, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": "%s, torch CPU fp32, %d threads, %s %dx%d, B=%d %s, %d timed steps after %d warm-up"
+                      % (what, cores, cfg["encoder"], cfg["H"], cfg["W"], B,
+                         "train step (fwd+silog+bwd+AdamW)" if train else "eval forward", len(times), warmup),
             "ms_per_step": 1e3 * total / len(times)}
 
 
-def lpg_roofline(torch, dev, pk):
-    """LPG-u microbench (BASELINE.json configs[4]), HBM regime: r=8/4/2 at 1024^2, batch 128 so the output is
-    512 MB (>> 126 MB L2; consecutive launches cannot hit in L2).  The kernels are launched through the C ABI
-    (bts_lpg_fwd / bts_lpg_bwd) back to back -- 20 launches between two CUDA events on the launching stream, so
-    the figure is the kernels' average duration, not Python launch latency.
-    Algorithmic bytes: fwd 4*px*(1+4/r^2), bwd 4*px*(1+8/r^2)  (BASELINE.md section 3)."""
-    import ctypes
+def gpu_reference_steps(cfg, torch, dev, steps=5, warmup=3):
+    """SURVEY 8d / BASELINE.md section 4 'second baseline (the bar to beat)': the reference model under stock torch-eager +
+    cuDNN on the same GPU -- fp32 with TF32 disabled (the parity-grade comparison) and with PyTorch's default
+    cudnn.allow_tf32=True (what a user gets out of the box), cudnn.benchmark=True as bts_main.py:402."""
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    m, crit, kind, what = _reference_model(cfg, torch)
+    train = cfg["train"]
+    m.to(dev)
+    m.train() if train else m.eval()
+    opt = make_optimizer(m, torch) if train else None
+    B = cfg["B"]
+    img, focal, gt = synth_batch(cfg, B, 1, dev)
+    st = torch.cuda.current_stream()
+
+    def step():
+        if train:
+            opt.zero_grad()
+            o = m(img, focal)
+            loss = crit(o[4], gt, gt > cfg["thr"])
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                m(img, focal)
+
+    try:
+        for label, tf32 in (("fp32", False), ("tf32_default", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(steps):
+                step()
+            e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[label] = {"value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["kind"] = kind
+    out["what"] = ("%s on cuda, torch-eager + cuDNN, cudnn.benchmark=True, %s %dx%d B=%d %s, %d timed steps after %d warm-up; "
+                   "fp32 = cudnn.allow_tf32 False (parity-grade), tf32_default = PyTorch's default cudnn.allow_tf32 True"
+                   % (what, cfg["encoder"], cfg["H"], cfg["W"], B, "train step" if train else "eval forward", steps, warmup))
+    del m, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ live peaks
+def tf32_peak(torch, secs=3.0, n=8192):
+    """TF32 dense GEMM peak, measured like MEASURED_PEAKS.json's bf16 figures (torch.matmul -> cuBLAS, 8192^3):
+    best of 10 = burst (for a kernel timed alone), back to back for `secs` s = sustained (for a kernel timed in a step)."""
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        c = torch.empty(n, n, device="cuda")
+        fl = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, k = time.time(), 0
+        e0.record()
+        while time.time() - t0 < secs:
+            for _ in range(20):
+                torch.matmul(a, b, out=c)
+            k += 20
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / k
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+    del a, b, c
+    torch.cuda.empty_cache()
+    return {"tf32_tflops": fl / best / 1e9, "tf32_tflops_sustained": fl / sus / 1e9,
+            "how": "torch.matmul fp32, allow_tf32 (cuBLAS TF32) %d^3: best of 10 (burst); back to back %.0f s (sustained)" % (n, secs)}
+
+
+# ------------------------------------------------------------------------------------------------ LPG microbench
+def _lpg_planes(torch, dev, Bn, h, w, r, max_depth):
     import math
+    g = torch.Generator(device=dev).manual_seed(r)
+    z = torch.randn(Bn, 3, h, w, device=dev, generator=g)
+    th = torch.sigmoid(z[:, 0]) * math.pi / 3
+    ph = torch.sigmoid(z[:, 1]) * math.pi * 2
+    return torch.stack([torch.sin(th) * torch.cos(ph), torch.sin(th) * torch.sin(ph), torch.cos(th),
+                        torch.sigmoid(z[:, 2]) * max_depth], 1).contiguous()
+
+
+def _lpg_time(torch, dev, Bn, side, r, reps=20, flush=None):
+    """average CUDA-event duration of bts_lpg_fwd / bts_lpg_bwd launched back to back through the C ABI.
+    flush: a buffer > L2 rewritten between launches (B=16 regime: working set < 126 MB L2, so each launch is timed alone)."""
+    import ctypes
     from bts_b200 import _lib
     L = _lib.lib()
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
     st = torch.cuda.current_stream()
     sp = ctypes.c_void_p(st.cuda_stream)
-    out = {}
-    side, Bn, reps = 1024, 128, 20
+    h = side // r
+    plane = _lpg_planes(torch, dev, Bn, h, h, r, 80.0)
     depth = torch.empty(Bn, side, side, device=dev)
     dy = torch.randn(Bn, side, side, device=dev)
-    for r in (8, 4, 2):
-        h = side // r
-        g = torch.Generator(device=dev).manual_seed(r)
-        z = torch.randn(Bn, 3, h, h, device=dev, generator=g)
-        th = torch.sigmoid(z[:, 0]) * math.pi / 3
-        ph = torch.sigmoid(z[:, 1]) * math.pi * 2
-        plane = torch.stack([torch.sin(th) * torch.cos(ph), torch.sin(th) * torch.sin(ph), torch.cos(th),
-                             torch.sigmoid(z[:, 2]) * MAX_DEPTH], 1).contiguous()
-        dplane = torch.empty_like(plane)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        for it in range(2):
-            if it == 1:
-                ev[0].record(st)
-            for _ in range(reps):
-                assert L.bts_lpg_fwd(vp(plane), vp(depth), Bn, h, h, r, 0, sp) == 0
-            if it == 1:
-                ev[1].record(st)
-            for _ in range(reps):
-                assert L.bts_lpg_bwd(vp(dy), vp(plane), vp(dplane), Bn, h, h, r, 0, 0, sp) == 0
-            if it == 1:
-                ev[2].record(st)
+    dplane = torch.empty_like(plane)
+    fwd = lambda: L.bts_lpg_fwd(vp(plane), vp(depth), Bn, h, h, r, 0, sp)
+    bwd = lambda: L.bts_lpg_bwd(vp(dy), vp(plane), vp(dplane), Bn, h, h, r, 0, 0, sp)
+    res = []
+    for fn in (fwd, bwd):
+        for _ in range(3):
+            assert fn() == 0
         torch.cuda.synchronize()
-        _lib.count(4 * reps)
-        mf, mb = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
-        px = Bn * side * side
-        bf, bb = 4.0 * px * (1 + 4.0 / r ** 2), 4.0 * px * (1 + 8.0 / r ** 2)
-        out["r%d" % r] = {"fwd_gbs": bf / mf / 1e6, "bwd_gbs": bb / mb / 1e6, "fwd_bwd_gbs": (bf + bb) / (mf + mb) / 1e6,
-                          "fwd_ms": mf, "bwd_ms": mb, "shape": [Bn, side, side]}
-        del plane, dplane, z
-    del depth, dy
+        if flush is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps):
+                fn()
+            e1.record(st)
+            torch.cuda.synchronize()
+            res.append(e0.elapsed_time(e1) / reps)
+        else:
+            ts = []
+            for _ in range(reps):
+                flush.add_(1.0)                           # evict L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                fn()
+                e1.record(st)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res.append(statistics.median(ts))
+        _lib.count(reps + 3)
+    px = float(Bn) * side * side
+    bf, bb = 4.0 * px * (1 + 4.0 / r ** 2), 4.0 * px * (1 + 8.0 / r ** 2)
+    mf, mb = res
+    del plane, depth, dy, dplane
+    return {"B": Bn, "side": side, "r": r, "fwd_ms": mf, "bwd_ms": mb, "fwd_gbs": bf / mf / 1e6, "bwd_gbs": bb / mb / 1e6,
+            "fwd_bwd_gbs": (bf + bb) / (mf + mb) / 1e6, "algorithmic_bytes": bf + bb}
+
+
+def lpg_roofline(torch, dev, pk):
+    """LPG fwd+bwd r=8/4/2 at 1024^2, batch 128: the output is 512 MB (>> 126 MB L2; consecutive launches cannot hit in
+    L2).  Algorithmic bytes: fwd 4*px*(1+4/r^2), bwd 4*px*(1+8/r^2)  (BASELINE.md section 3)."""
+    out = {}
+    for r in (8, 4, 2):
+        t = _lpg_time(torch, dev, 128, 1024, r)
+        out["r%d" % r] = t
     torch.cuda.empty_cache()
     a = out["r8"]["fwd_bwd_gbs"]
     return {"bound": "hbm", "kernel": "lpg_fwd_vec<8> + lpg_bwd_vec<8> (fwd+bwd, r=8, 128x1024x1024, output 512 MB >> L2, "
-                                      "20 back-to-back launches each)",
+                                      "20 back-to-back launches each, timed in isolation -> burst peak)",
             "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a / pk["hbm_gbs"], "peak_source": pk["source"],
             # dram__bytes_read.sum + dram__bytes_write.sum of one (fwd, bwd) launch pair, `ncu --set full` capture
             # profiles/r01_lpg_r8_v2.ncu-rep of this same microbench: fwd 33.6 + 479.3 MB, bwd 570.4 + 32.3 MB
-            # (algorithmic 570.4 + 604.0 MB: no re-reads; part of the forward's output is still dirty in L2 at kernel end)
             "traffic": 1115.6e6, "traffic_unit": "bytes per fwd+bwd launch pair (ncu, profiles/r01_lpg_r8_v2.ncu-rep)",
-            "algorithmic_bytes": (4.0 * 128 * 1024 * 1024) * ((1 + 4.0 / 64) + (1 + 8.0 / 64)), "sweep": out}
+            "algorithmic_bytes": out["r8"]["algorithmic_bytes"], "sweep": out}
 
 
-def conv_roofline(torch, dev, pk):
-    """The dominant kernel of the step by time is the conv engine (conv_tc_kernel: every forward and dgrad).  One of its
-    layers, timed live: daspp_conv 896->128 3x3 at 44x88, batch 16 (input 222 MB > 126 MB L2, so consecutive launches
-    cannot be served from L2), 20 back-to-back launches between two CUDA events on the launching stream.
-    achieved = nominal dense FLOPs (2*B*H*W*Cout*Cin*9) / average launch time; peak = the parity-mode (3xTF32) tensor
-    roof derived from the measured bf16 throughput: bf16 / 2 (tf32) / 3 (three products)."""
-    from bts_b200 import conv
-    B, Cin, H, W, Cout, k = 16, 896, 44, 88, 128, 3
-    g = torch.Generator(device=dev).manual_seed(3)
-    x = torch.randn(B, Cin, H, W, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
-    w = torch.randn(Cout, Cin, k, k, device=dev, generator=g) / (Cin * k * k) ** 0.5
-    packed = conv.pack_weights(w)
-    run = lambda: conv.conv2d_tc(x, w, 1, 1, 1, packed=packed)
-    reps = 20
-    run()
-    run()
-    torch.cuda.synchronize()
-    st = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(reps):
-        run()
-    e1.record(st)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * B * H * W * Cout * Cin * k * k
-    a = flops / ms / 1e9
-    peak = pk["bf16_tflops"] / 6.0
-    del x, w, packed
-    torch.cuda.empty_cache()
-    return {"bound": "tensor", "kernel": "conv_tc_kernel, daspp_conv 896->128 3x3 @16x44x88 (3xTF32, N-stacked hi/lo MMAs), "
-                                         "%d back-to-back launches" % reps,
-            "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak, "ms_per_launch": ms,
-            "peak_source": "bf16 sustained / 2 / 3; " + pk["source"], "traffic": None,
-            "algorithmic_flops": flops}
+def run_lpg_config(args):
+    """--config LPG (BASELINE.json configs[4]): r in {8,4,2} x H=W in {256,384,512,768,1024}; two regimes per point:
+    'hbm' = batch sized so the output is >= 512 MB (working set >> L2), 'b16' = batch 16 with an L2 flush between launches."""
+    import torch
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from bts_b200 import _lib
+    _lib.lib()
+    pk = peaks()
+    flush = torch.zeros(64 * 1024 * 1024, device=dev)         # 256 MB > 126 MB L2
+    rows = []
+    l0 = _lib.launches
+    for r in (8, 4, 2):
+        for side in (256, 384, 512, 768, 1024):
+            Bh = max(16, (512 * 1024 * 1024 + 4 * side * side - 1) // (4 * side * side))
+            a = _lpg_time(torch, dev, Bh, side, r)
+            b = _lpg_time(torch, dev, 16, side, r, reps=10, flush=flush)
+            rows.append({"r": r, "side": side, "hbm": {k: a[k] for k in ("B", "fwd_ms", "bwd_ms", "fwd_gbs", "bwd_gbs", "fwd_bwd_gbs")},
+                         "b16": {k: b[k] for k in ("B", "fwd_ms", "bwd_ms", "fwd_gbs", "bwd_gbs", "fwd_bwd_gbs")}})
+            torch.cuda.empty_cache()
+    vals = [x["hbm"]["fwd_bwd_gbs"] for x in rows]
+    res = {"metric": "LPG fwd+bwd GB/s vs HBM peak", "value": statistics.median(vals), "unit": "GB/s", "n_gpus": 1,
+           "steps": 20, "warmup": 3, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "LPG-u: plane-to-depth fwd+bwd, r=8/4/2, H=W 256..1024, 1 GPU; value = median over the 15 "
+                                  "HBM-regime points", "l2": "hbm regime: outputs >= 512 MB; b16 regime: 256 MB flush write between launches"},
+           "roofline": {"bound": "hbm", "achieved": statistics.median(vals), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": statistics.median(vals) / pk["hbm_gbs"], "min_frac": min(vals) / pk["hbm_gbs"],
+                        "peak_source": pk["source"], "traffic": None},
+           "gpu_launches": _lib.launches - l0, "sweep": rows}
+    return res
 
 
 class StdoutToStderr:
@@ -280,6 +454,12 @@ class StdoutToStderr:
 
 
 def run_ours(args):
+    if args.config == "LPG":
+        if int(os.environ.get("RANK", "0")) == 0:       # single-GPU microbench (BASELINE.json configs[4]: "1 GPU")
+            with StdoutToStderr():
+                res = run_lpg_config(args)
+            print(json.dumps(res), flush=True)
+        return
     with StdoutToStderr():
         res, rank, dist = _run_ours(args)
     if rank == 0:
@@ -289,9 +469,44 @@ def run_ours(args):
             dist.destroy_process_group()
 
 
+def conv_rooflines(torch, conv, step_fn, pk_tf32):
+    """One extra, untimed training step with CUDA events around every engine call (bts_b200.conv trace): the dominant
+    kernel's nominal FLOPs over all its launches in the step / the sum of their durations (FLOP-weighted by construction)."""
+    conv.set_trace(True)
+    try:
+        step_fn()
+        rep = conv.trace_report()
+    finally:
+        conv.set_trace(False)
+    agg = {}
+    for t, n, (kind, desc), fl in rep:
+        g = {"fwd": "conv", "dgrad": "conv", "wgrad": "wgrad"}.get(kind)
+        if g is None:
+            continue
+        a = agg.setdefault(g, {"ms": 0.0, "launches": 0, "flops": 0.0, "layers": []})
+        a["ms"] += t
+        a["launches"] += n
+        a["flops"] += fl
+        a["layers"].append((t, n, kind, desc, fl))
+    peak = pk_tf32["tf32_tflops_sustained"] / 3.0
+    out = {}
+    for g, a in agg.items():
+        ach = a["flops"] / a["ms"] / 1e9 if a["ms"] > 0 else 0.0
+        top = sorted(a["layers"], reverse=True)[:6]
+        out[g] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                  "launches_per_step": a["launches"], "ms_per_step": a["ms"],
+                  "avg_launch_ms": a["ms"] / max(1, a["launches"]), "algorithmic_flops_per_step": a["flops"],
+                  "peak_source": "parity mode 3xTF32: TF32 GEMM peak measured live by this run (sustained, the kernel is timed "
+                                 "inside a long step) / 3 products",
+                  "top_layers": [{"kind": k, "layer": d, "calls": n, "ms": round(t, 3), "tflops": round(fl / t / 1e9, 1)}
+                                 for t, n, k, d, fl in top]}
+    return out
+
+
 def _run_ours(args):
     import torch
     import torch.distributed as dist
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,34 +518,41 @@ def _run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     import bts
-    from bts_b200 import _lib
+    from bts_b200 import _lib, conv
     _lib.lib()                                   # fail loudly if the CUDA library is missing
     torch.backends.cudnn.benchmark = True        # bts_main.py:402
     torch.manual_seed(0)
-    p = types.SimpleNamespace(encoder="densenet161_bts", max_depth=MAX_DEPTH, dataset="kitti", bts_size=512,
+    p = types.SimpleNamespace(encoder=cfg["encoder"], max_depth=cfg["max_depth"], dataset=cfg["dataset"], bts_size=512,
                               pretrained=False)
     model = bts.BtsModel(p)
-    model.train()
-    model.decoder.apply(bts.weights_init_xavier)
-    freeze_like_set_misc(model)
+    train = cfg["train"]
+    if train:
+        model.train()
+        model.decoder.apply(bts.weights_init_xavier)
+        freeze_like_set_misc(model)
+    else:
+        model.eval()
     model.to(dev)
-    if world > 1:
+    if world > 1 and train:
         # bts_main.py:352 passes find_unused_parameters=True because the ResNet/ResNeXt encoders keep a never-used `fc`
         # (SURVEY Q11); DenseNet-161 has no unused parameter, so the extra autograd traversal is switched off here.
         unused = any(k.startswith("encoder.base_model.fc") for k, _ in model.named_parameters())
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=unused,
                                                           gradient_as_bucket_view=True)
-    opt = make_optimizer(model, torch)
+    opt = make_optimizer(model, torch) if train else None
     crit = bts.silog_loss(0.85)
-    B = B_PER_GPU
-    img, focal, gt = synth_batch(B, 1 + rank, dev)
-    himg, hfocal, hgt = synth_batch(B, 1 + rank, pin=True)
+    B = cfg["B"]
+    img, focal, gt = synth_batch(cfg, B, 1 + rank, dev)
+    himg, hfocal, hgt = synth_batch(cfg, B, 1 + rank, pin=True)
     total_steps = 10000
 
     def step(i, x, f, g):
+        if not train:
+            with torch.no_grad():
+                return model(x, f)[4].sum()
         opt.zero_grad()
         out = model(x, f)
-        loss = crit(out[4], g, g > 1.0)
+        loss = crit(out[4], g, g > cfg["thr"])
         loss.backward()
         lr = (1e-4 - 1e-5) * (1 - i / total_steps) ** 0.9 + 1e-5
         for grp in opt.param_groups:
@@ -347,65 +569,91 @@ def _run_ours(args):
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if rank == 0 else None
         l0 = _lib.launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = torch.cuda.current_stream()
-        e0.record(st)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        marks[0].record(st)
         for i in range(K):
             fn(Wm + i)
-        e1.record(st)
+            marks[i + 1].record(st)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([marks[0].elapsed_time(marks[K])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
         clocks = sampler.stop() if sampler else None
-        return float(ms), _lib.launches - l0, clocks
+        return float(ms), _lib.launches - l0, clocks, per
 
     K, Wm = args.steps, max(args.warmup, 3)
-    ms, launches, clocks = timed(lambda i: step(i, img, focal, gt), K, Wm)
+    ms, launches, clocks, per = timed(lambda i: step(i, img, focal, gt), K, Wm)
 
     def e2e_step(i):
         x = himg.to(dev, non_blocking=True)
         f = hfocal.to(dev, non_blocking=True)
         g = hgt.to(dev, non_blocking=True)
-        return float(step(i, x, f, g).detach())  # D2H read of the loss every step (bts_main.py:463)
+        return float(step(i, x, f, g).detach())  # D2H read of the loss (bts_main.py:463) / of the result every step
 
-    ms_e, _, _ = timed(e2e_step, K, 1)
+    ms_e, _, _, per_e = timed(e2e_step, K, 1)
     h2d = himg.numel() * 4 + hfocal.numel() * 8 + hgt.numel() * 4
 
     pk = peaks()
     res = {
-        "metric": "training images/sec (352x704, DenseNet-161)", "value": world * B * K / (ms / 1e3), "unit": "images/s",
+        "metric": cfg["metric"], "value": world * B * K / (ms / 1e3), "unit": "images/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "K16: DenseNet-161 encoder, 352x704 KITTI-shape synthetic, batch 16/GPU, train step "
-                               "(fwd + silog + bwd + AdamW), random-init weights",
-                   "global_batch": world * B, "parallelism": "dp%d" % world,
-                   "l2": "no explicit flush: per-step working set (~31 GB saved activations) >> 126 MB L2",
-                   "conv_path": os.environ.get("BTS_B200_CONV", "auto")},
+        "config": {"workload": cfg["workload"], "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "no explicit flush: per-step working set (saved activations, GBs) >> 126 MB L2",
+                   "precision": "3xTF32 split on tcgen05 (fp32-grade, parity mode)"},
         "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e / K},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e / K, "ms_per_step_median": statistics.median(per_e)},
+        "repeats": {"ms_per_step_median": statistics.median(per), "ms_per_step_min": per[0], "ms_per_step_max": per[-1],
+                    "n": K, "note": "rank-0 per-step CUDA-event durations inside the timed region"},
         "gpu_launches": launches, "clocks": clocks,
     }
     if rank == 0:
-        res["roofline_step"] = {"bound": "tensor", "achieved": res["value"] / world * GFLOP_PER_IMG_TRAIN / 1e3,
-                                "unit": "TFLOP/s per GPU (nominal conv FLOPs 588 GFLOP/img)",
-                                "peak": pk["bf16_tflops"] / 2.0 / 3.0,
-                                "peak_note": "parity-grade 3xTF32 = (bf16 sustained / 2) / 3; " + pk["source"],
-                                "frac": res["value"] / world * GFLOP_PER_IMG_TRAIN / 1e3 / (pk["bf16_tflops"] / 6.0)}
-        if world == 1:
-            if not args.no_lpg:
-                del model, opt
-                torch.cuda.empty_cache()
-                res["roofline"] = lpg_roofline(torch, dev, pk)
+        res["roofline_step"] = {"bound": "tensor", "achieved": res["value"] / world * cfg["gflop"] / 1e3,
+                                "unit": "TFLOP/s per GPU (nominal conv FLOPs %.1f GFLOP/img)" % cfg["gflop"]}
+        if world == 1 and not args.no_roofline:
+            try:
+                live = tf32_peak(torch)
+            except Exception as e:                 # an evidence leg must never cost the bench line
+                live = {"tf32_tflops": pk["bf16_tflops"] / 2.0, "tf32_tflops_sustained": pk["bf16_tflops_sustained"] / 2.0,
+                        "how": "FAILED (%s): derived bf16/2 from %s" % (e, pk["source"])}
+            res["peaks_live"] = dict(live, hbm_gbs=pk["hbm_gbs"], bf16_tflops=pk["bf16_tflops"],
+                                     bf16_tflops_sustained=pk["bf16_tflops_sustained"], hbm_bf16_source=pk["source"])
+            roof3 = live["tf32_tflops_sustained"] / 3.0
+            res["roofline_step"].update(peak=roof3, frac=res["roofline_step"]["achieved"] / roof3,
+                                        peak_note="parity-grade 3xTF32 = TF32 GEMM peak measured live (sustained) / 3")
+            if train:
                 try:
-                    res["roofline_conv"] = conv_roofline(torch, dev, pk)
-                except Exception as e:             # an evidence leg must never cost the bench line
-                    res["roofline_conv"] = {"error": "%s: %s" % (type(e).__name__, e)}
+                    rl = conv_rooflines(torch, conv, lambda: step(Wm + K, img, focal, gt), live)
+                    if "conv" in rl:
+                        res["roofline"] = dict(rl["conv"], kernel="conv_tc_kernel (tcgen05 implicit GEMM: every conv forward and "
+                                                                  "dgrad of the step), all launches of one real training step",
+                                               # ncu --set full, profiles/r01_conv5_v4.ncu-rep: conv5 896->512 @22x44x16, one launch:
+                                               # 115.0 MB read + 10.7 MB written vs 88 MB algorithmic (input 55.5 + output 31.7 + weights)
+                                               traffic=125.7e6, traffic_unit="bytes, ONE launch of the conv5 layer (ncu capture "
+                                                                             "profiles/r01_conv5_v4.ncu-rep; algorithmic 88 MB)")
+                    if "wgrad" in rl:
+                        res["roofline_wgrad"] = dict(rl["wgrad"], kernel="wgrad kernels (tcgen05, MN-major operands), all launches "
+                                                                         "of one real training step", traffic=None)
+                except Exception as e:
+                    res["roofline"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            del model, opt
+            torch.cuda.empty_cache()
+            if not args.no_lpg:
+                res["roofline_lpg"] = lpg_roofline(torch, dev, pk)
+            if "roofline" not in res and "roofline_lpg" in res:
+                res["roofline"] = res["roofline_lpg"]          # forward-only config: the HBM-bound LPG pair
+            if not args.no_gpu_baseline:
+                try:
+                    res["gpu_baseline"] = gpu_reference_steps(cfg, torch, dev)
+                except Exception as e:
+                    res["gpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
             if not args.no_cpu:
-                res["cpu_baseline"] = cpu_reference_steps(3, 1)
+                res["cpu_baseline"] = cpu_reference_steps(cfg, 3, 1)
     return res, rank, (dist if world > 1 else None)
 
 
@@ -413,14 +661,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config if args.config in CONFIGS else "K16"]
     with StdoutToStderr():
-        r = cpu_reference_steps(args.steps, args.warmup)
-    res = {"impl": "reference", "metric": "training images/sec (352x704, DenseNet-161)", "value": r["value"],
+        r = cpu_reference_steps(cfg, args.steps, args.warmup)
+    res = {"impl": "reference", "metric": cfg["metric"], "value": r["value"],
            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "K16: DenseNet-161 encoder, 352x704 KITTI-shape synthetic, train step "
-                                  "(fwd + silog + bwd + AdamW); CPU sample batch = 2 images/step"},
+           "config": {"workload": cfg["workload"] + "; CPU sample: " + r["sample"]},
            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(res), flush=True)
@@ -432,8 +680,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="K16", choices=sorted(CONFIGS) + ["LPG"])
     ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager/cuDNN reference leg")
+    ap.add_argument("--no-roofline", action="store_true", help="skip every evidence leg (peaks, traced step, LPG, baselines)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,33 +15,40 @@ from .ops import _need_cuda, _ptr, _stream
 
 ACT = {None: 0, "none": 0, "elu": 1, "sigmoid": 2}
 import os as _os
-WGRAD_BACKEND = _os.environ.get("BTS_B200_WGRAD", "tc")     # tc: tcgen05 wgrad kernel | aten: library scaffold
 
-PW_WGRAD = _os.environ.get("BTS_B200_PW_WGRAD", "1") == "1"   # CUDA-core wgrad for narrow 1x1 layers (csrc/pointwise.cu)
+PW_WGRAD = True                                               # CUDA-core wgrad for narrow 1x1 layers (csrc/pointwise.cu)
 PW_MIN_PIXELS = 200000                                        # below this the tensor-core path is already short
 TRACE = _os.environ.get("BTS_B200_TRACE", "0") == "1"     # per-call CUDA-event timing, aggregated by shape
 trace_log = []
 
 
-def _traced(kind, desc, fn):
+def set_trace(on):
+    """bench.py / tools: CUDA events around every engine call (measurement only; never on in the timed region)"""
+    global TRACE
+    TRACE = bool(on)
+    del trace_log[:]
+
+
+def _traced(kind, desc, fn, flops=0.0):
     if not TRACE:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = fn()
     e1.record()
-    trace_log.append((kind, desc, e0, e1))
+    trace_log.append((kind, desc, flops, e0, e1))
     return out
 
 
 def trace_report():
+    """[(total ms, calls, (kind, desc), total nominal FLOPs)] sorted by time"""
     torch.cuda.synchronize()
     agg = {}
-    for kind, desc, e0, e1 in trace_log:
+    for kind, desc, flops, e0, e1 in trace_log:
         k = (kind, desc)
-        t, n = agg.get(k, (0.0, 0))
-        agg[k] = (t + e0.elapsed_time(e1), n + 1)
-    return sorted(((t, n, k) for k, (t, n) in agg.items()), reverse=True)
+        t, n, f = agg.get(k, (0.0, 0, 0.0))
+        agg[k] = (t + e0.elapsed_time(e1), n + 1, f + flops)
+    return sorted(((t, n, k, f) for k, (t, n, f) in agg.items()), reverse=True)
 
 
 _pack_cache = {}   # id(weight) -> (weakref, version, data_ptr, transpose) -> packed tensor
@@ -137,7 +144,7 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
                                                          int(precision), _ptr(stats[0]), _ptr(stats[1]), _stream())
         rc = _traced("dgrad" if transpose_flip else "fwd",
                      "%dx%dx%d %d->%d k%d d%d s%d%s" % (B, Hs, Ws, Cin, Co, KH, dilation, stride, " up" if upsample2 else ""),
-                     call)
+                     call, 2.0 * B * Hout * Wout * Co * Cin * KH * KW)
     _lib.check(rc, "bts_conv_fwd")
     _lib.count()
     return out
@@ -160,7 +167,8 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
         with torch.cuda.device(x.device):
             rc = _traced("pwwgrad", "%dx%dx%d %d->%d k1" % (B, Hs, Ws, Cin, Cout),
                          lambda: L.bts_conv_pw_wgrad(_ptr(x), xs, _ptr(gy), gs, B * Hs * Ws, Cin, Cout, _ptr(ws), _ptr(gw),
-                                                     weight_strides[0], weight_strides[1], _stream()))
+                                                     weight_strides[0], weight_strides[1], _stream()),
+                         2.0 * B * Hs * Ws * Cout * Cin)
         _lib.check(rc, "bts_conv_pw_wgrad")
         _lib.count(2)
         return gw
@@ -179,7 +187,8 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
                      lambda: L.bts_conv_wgrad(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
                                               dilation, _ptr(pre_scale), _ptr(pre_shift), int(pre_relu), _ptr(gy), gs,
                                               Cout, _ptr(ws), split.value, _ptr(gw), s[0], s[1], s[2], s[3],
-                                              int(precision), _stream()))
+                                              int(precision), _stream()),
+                     2.0 * B * gy.shape[2] * gy.shape[3] * Cout * Cin * KH * KW)
     _lib.check(rc, "bts_conv_wgrad")
     _lib.count(2)
     return gw
@@ -209,12 +218,7 @@ class _ConvTC(torch.autograd.Function):
                 gx = torch.ops.aten.convolution_backward(gy, x, weight, None, [stride] * 2, [padding] * 2, [dilation] * 2,
                                                          False, [0, 0], 1, [True, False, False])[0]
         if ctx.needs_input_grad[1]:
-            if WGRAD_BACKEND == "tc":
-                gw = wgrad_tc(x, gy, weight.shape, weight.stride(), stride, padding, dilation)
-            else:
-                gw = torch.ops.aten.convolution_backward(gy.contiguous(memory_format=torch.channels_last), x, weight,
-                                                         None, [stride] * 2, [padding] * 2, [dilation] * 2, False,
-                                                         [0, 0], 1, [False, True, False])[1]
+            gw = wgrad_tc(x, gy, weight.shape, weight.stride(), stride, padding, dilation)
         return gx, gw, None, None, None
 
 

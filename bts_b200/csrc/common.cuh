@@ -17,3 +17,6 @@ __host__ __device__ constexpr int bts_ceil_div(long long a, long long b) { retur
 
 // number of SMs of the current device (cached); grids of persistent kernels are sized from it
 int bts_num_sms();
+// current device ordinal (mod BTS_MAX_DEVICES): key of per-device one-time setup (cudaFuncSetAttribute is per device)
+constexpr int BTS_MAX_DEVICES = 64;
+int bts_cur_device();

@@ -431,7 +431,7 @@ int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int u
     cudaError_t err = cudaSuccess;
 #define BTS_LAUNCH(PRE, UP, VEC)                                                                                      \
     do {                                                                                                              \
-        static int attr_smem = 0;                                                                                     \
+        static int attr_smem_[BTS_MAX_DEVICES] = {}; int &attr_smem = attr_smem_[bts_cur_device()];                                                                                   \
         if (attr_smem < smem) {                                                                                       \
             err = cudaFuncSetAttribute(wgrad2_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                        SMEM_BUDGET + 2 * BLOCK_CI * 4 + 256 + 1024);                                  \

@@ -531,7 +531,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     cudaError_t err = cudaSuccess;
 #define BTS_LAUNCH(PRE, UP, VEC)                                                                                    \
     do {                                                                                                            \
-        static bool attr_set = false;                                                                               \
+        static bool attr_set_[BTS_MAX_DEVICES] = {}; bool &attr_set = attr_set_[bts_cur_device()];                                                                             \
         if (!attr_set) {                                                                                            \
             err = cudaFuncSetAttribute(wgrad_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                        SMEM_LIMIT);                                                                 \

@@ -23,8 +23,7 @@ import torch
 from . import _lib, conv
 from .ops import _ptr, _stream
 
-FUSE = os.environ.get("BTS_B200_FUSE", "1") == "1"
-EPI_STATS = os.environ.get("BTS_B200_EPI_STATS", "1") == "1"   # BatchNorm batch statistics reduced in the conv epilogue
+EPI_STATS = True   # BatchNorm batch statistics reduced in the producing conv's epilogue (csrc/conv_tc.cu)
 
 
 def _view(t):
@@ -177,7 +176,7 @@ def dense_block_forward(block, x):
 
 
 def dense_block_eligible(block, x):
-    if not (FUSE and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
         return False
     for layer in block.children():
         ok = (hasattr(layer, "norm1") and hasattr(layer, "conv2") and layer.conv1.kernel_size == (1, 1)

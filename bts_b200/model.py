@@ -46,9 +46,11 @@ class silog_loss(nn.Module):
         return ops.silog(depth_est, depth_gt, mask, self.variance_focus)
 
 
-def conv_backend():
-    """BTS_B200_CONV = tc (tcgen05 implicit-GEMM engine, bts_b200/csrc/conv_tc.cu) | cudnn (library scaffold)."""
-    return os.environ.get("BTS_B200_CONV", "tc")
+def _require_cuda_fp32(x, what):
+    """the product path has no CPU / eager / library fallback (north_star): fail loudly instead of silently diverging"""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        raise RuntimeError("bts_b200.%s runs on CUDA fp32 NCHW/NHWC tensors only (got device=%s dtype=%s dim=%d); there is "
+                           "no CPU or library fallback" % (what, x.device, x.dtype, x.dim()))
 
 
 class Conv2dTC(nn.Conv2d):
@@ -56,7 +58,7 @@ class Conv2dTC(nn.Conv2d):
     weights_init_xavier (bts_main.py:338), state_dict keys and optimizer groups behave exactly as in the reference."""
 
     def forward(self, x):
-        if (conv_backend() == "tc" and x.is_cuda and x.dtype == torch.float32 and self.groups == 1
+        if (x.is_cuda and x.dtype == torch.float32 and self.groups == 1
                 and self.bias is None and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
                 and self.dilation[0] == self.dilation[1] and self.kernel_size[0] == self.kernel_size[1]
                 and isinstance(self.padding, tuple) and self.padding_mode == "zeros"):
@@ -64,11 +66,13 @@ class Conv2dTC(nn.Conv2d):
             if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
                 return conv.conv_c1(x, self.weight, sigmoid=False)
             return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0])
-        return super().forward(x)
+        # shapes the engine does not cover (bias / asymmetric geometry): the library conv, pinned to true fp32 for parity
+        with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=False):
+            return super().forward(x)
 
     def forward_sigmoid(self, x):
         """conv + Sigmoid in one kernel when this is a single-output-channel head (get_depth, reduc1x1.final)."""
-        if conv_backend() == "tc" and x.is_cuda and x.dtype == torch.float32:
+        if x.is_cuda and x.dtype == torch.float32:
             from . import conv
             if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
                 return conv.conv_c1(x, self.weight, sigmoid=True)
@@ -77,8 +81,8 @@ class Conv2dTC(nn.Conv2d):
 
 def fuse_enabled(x):
     """the fused glue path (bts_b200/glue.py) is taken for fp32 CUDA tensors when the tensor-core backend is active"""
-    from . import fused, glue
-    return fused.FUSE and conv_backend() == "tc" and glue.eligible(x)
+    from . import glue
+    return glue.eligible(x)
 
 
 class BatchNormTC(nn.BatchNorm2d):
@@ -90,7 +94,7 @@ class BatchNormTC(nn.BatchNorm2d):
         if fuse_enabled(x) and self.affine:
             from . import glue
             return glue.bn_act(x, self, relu=self._fuse_relu)
-        y = super().forward(x)
+        y = super().forward(x)                     # non-affine / non-fp32 BatchNorm: not on the BTS path
         return F.relu(y) if self._fuse_relu else y
 
 
@@ -123,7 +127,7 @@ def _dense_block_class():
 
         def forward(self, init_features):
             from . import fused
-            if conv_backend() == "tc" and fused.dense_block_eligible(self, init_features):
+            if fused.dense_block_eligible(self, init_features):
                 return fused.dense_block_forward(self, init_features)
             return super().forward(init_features)
 
@@ -176,15 +180,14 @@ class atrous_conv(nn.Sequential):
         self.atrous_conv = body
 
     def forward(self, x):
-        if fuse_enabled(x):
-            from . import glue
-            seq = self.atrous_conv.aconv_sequence
-            if hasattr(self.atrous_conv, "first_bn"):
-                b = glue.bn_relu_conv(x, self.atrous_conv.first_bn, seq[1].weight)
-            else:
-                b = glue.conv_act(x, seq[1].weight, pre_relu=True)
-            return glue.bn_relu_conv(b, seq[2], seq[4].weight, seq[4].padding[0], seq[4].dilation[0])
-        return self.atrous_conv(x)
+        _require_cuda_fp32(x, "atrous_conv")
+        from . import glue
+        seq = self.atrous_conv.aconv_sequence
+        if hasattr(self.atrous_conv, "first_bn"):
+            b = glue.bn_relu_conv(x, self.atrous_conv.first_bn, seq[1].weight)
+        else:
+            b = glue.conv_act(x, seq[1].weight, pre_relu=True)
+        return glue.bn_relu_conv(b, seq[2], seq[4].weight, seq[4].padding[0], seq[4].dilation[0])
 
 
 class upconv(nn.Module):
@@ -197,12 +200,15 @@ class upconv(nn.Module):
         self.ratio = ratio
 
     def forward(self, x, pre_relu=False):
-        if fuse_enabled(x) and self.ratio == 2:
-            from . import glue                   # up-sample folded into the im2col map, ELU in the epilogue
+        _require_cuda_fp32(x, "upconv")
+        from . import glue
+        if self.ratio == 2:                      # up-sample folded into the im2col map, ELU in the epilogue
             return glue.conv_act(x, self.conv.weight, 1, 1, pre_relu=pre_relu, up=True, act="elu")
+        # other ratios never occur in BTS (bts.py:153-189 always uses 2): materialise the up-sample, conv + ELU on the engine
         if pre_relu:
             x = F.relu(x)
-        return self.elu(self.conv(F.interpolate(x, scale_factor=self.ratio, mode="nearest")))
+        x = F.interpolate(x, scale_factor=self.ratio, mode="nearest").contiguous(memory_format=torch.channels_last)
+        return glue.conv_act(x, self.conv.weight, 1, 1, act="elu")
 
 
 class reduction_1x1(nn.Sequential):
@@ -228,19 +234,15 @@ class reduction_1x1(nn.Sequential):
             cin, cout = cout, cout // 2
 
     def trunk(self, net):
-        fuse = fuse_enabled(net)
-        glue = None
-        if fuse:
-            from . import glue
+        _require_cuda_fp32(net, "reduction_1x1")
+        from . import glue
         for name, m in self.reduc.named_children():
             if name == "final":                 # Sequential(1x1 conv 8->1, Sigmoid): fused single-channel head kernel
                 net = m[0].forward_sigmoid(net)
             elif name == "plane_params":
                 net = m(net)
-            elif fuse:                          # Sequential(1x1 conv, ELU): ELU in the conv epilogue
+            else:                               # Sequential(1x1 conv, ELU): ELU in the conv epilogue
                 net = glue.conv_act(net, m[0].weight, 0, 1, act="elu")
-            else:
-                net = m(net)
         return net
 
     def forward(self, net):
@@ -266,18 +268,6 @@ class local_planar_guidance(nn.Module):
 
     def forward(self, plane_eq, focal=None):
         return ops.lpg(plane_eq, int(self.upratio))
-
-
-def _cat_pad4(tensors):
-    """torch.cat along channels whose result has 16-byte aligned NHWC rows: when the channel sum is not a multiple
-    of 4 (concat3: 225, concat2: 161) the slab gets zero channels appended and a view of the real ones is returned,
-    so the conv engine's 128-bit loads apply (the kernel masks the channel tail)."""
-    C = sum(t.shape[1] for t in tensors)
-    if C % 4 == 0 or not tensors[0].is_cuda:
-        return torch.cat(tensors, 1)
-    B, _, H, W = tensors[0].shape
-    pad = tensors[0].new_zeros((B, 4 - C % 4, H, W))
-    return torch.cat(list(tensors) + [pad], 1)[:, :C]
 
 
 class bts(nn.Module):
@@ -318,9 +308,8 @@ class bts(nn.Module):
         self.get_depth = nn.Sequential(_conv(nf // 16, 1, 3), nn.Sigmoid())
 
     def forward(self, features, focal):
-        if fuse_enabled(features[4]):
-            return self._forward_fused(features, focal)
-        return self._forward_eager(features, focal)
+        _require_cuda_fp32(features[4], "bts.forward")
+        return self._forward_fused(features, focal)
 
     def _forward_fused(self, features, focal):
         """bts.forward (reference pytorch/bts.py:196-266) over the fused units of bts_b200/glue.py: no ATen BatchNorm /
@@ -356,39 +345,6 @@ class bts(nn.Module):
             final_depth = final_depth * focal.view(-1, 1, 1, 1).float() / 715.0873
         return depth_8x8_scaled, depth_4x4_scaled, depth_2x2_scaled, reduc1x1, final_depth
 
-    def _forward_eager(self, features, focal):
-        skip0, skip1, skip2, skip3 = features[0], features[1], features[2], features[3]
-        md = self.params.max_depth
-        x = self.bn5(self.upconv5(features[4], pre_relu=True))                                   # H/16
-        x = self.conv5(torch.cat([x, skip3], 1))
-        cat4 = torch.cat([self.bn4(self.upconv4(x)), skip2], 1)                           # H/8
-        iconv4 = self.bn4_2(self.conv4(cat4))
-        d3 = self.daspp_3(iconv4)
-        grow = torch.cat([cat4, d3], 1)
-        d6 = self.daspp_6(grow)
-        grow = torch.cat([grow, d6], 1)
-        d12 = self.daspp_12(grow)
-        grow = torch.cat([grow, d12], 1)
-        d18 = self.daspp_18(grow)
-        grow = torch.cat([grow, d18], 1)
-        d24 = self.daspp_24(grow)
-        feat8 = self.daspp_conv(torch.cat([iconv4, d3, d6, d12, d18, d24], 1))
-
-        depth_8x8_scaled, d8_ds = ops.plane_head_lpg(self.reduc8x8.trunk(feat8), 8, md, ds_stride=4)
-        x = self.bn3(self.upconv3(feat8))                                                 # H/4
-        iconv3 = self.conv3(_cat_pad4([x, skip1, d8_ds]))
-        depth_4x4_scaled, d4_ds = ops.plane_head_lpg(self.reduc4x4.trunk(iconv3), 4, md, ds_stride=2)
-        x = self.bn2(self.upconv2(iconv3))                                                # H/2
-        iconv2 = self.conv2(_cat_pad4([x, skip0, d4_ds]))
-        depth_2x2_scaled = ops.plane_head_lpg(self.reduc2x2.trunk(iconv2), 2, md)
-        up1 = self.upconv1(iconv2)                                                        # H
-        reduc1x1 = self.reduc1x1(up1)
-        iconv1 = self.conv1(torch.cat([up1, reduc1x1, depth_2x2_scaled, depth_4x4_scaled, depth_8x8_scaled], 1))
-        final_depth = md * self.get_depth[0].forward_sigmoid(iconv1)      # Sequential(3x3 conv 32->1, Sigmoid), fused
-        if self.params.dataset == "kitti":
-            final_depth = final_depth * focal.view(-1, 1, 1, 1).float() / 715.0873
-        return depth_8x8_scaled, depth_4x4_scaled, depth_2x2_scaled, reduc1x1, final_depth
-
 
 _ENCODERS = {
     # params.encoder: (torchvision ctor, use .features, skip tap names, skip channels)   reference bts.py:273-300
@@ -403,27 +359,35 @@ _ENCODERS = {
 
 
 def _load_backbone(ctor, pretrained):
-    """The reference asks torchvision for ImageNet weights (pretrained=True, bts.py:274-298).  We honour that
-    when the checkpoint is already in the local torch-hub cache (or params.pretrained=True forces a download);
-    offline with an empty cache -- the benchmark / test condition -- the backbone is random-initialised."""
-    import os
+    """The reference builds the backbone with `pretrained=True` (bts.py:274-298), which torchvision maps to the
+    IMAGENET1K_V1 weights and downloads into the torch-hub cache when they are not there yet.  Same here by default
+    (params.pretrained absent / None / True).  Random init is OPT-IN: params.pretrained=False (bench.py, the tests) or
+    BTS_B200_PRETRAINED=0.  If the weights can be neither found nor downloaded (offline box) the encoder falls back to
+    random init with a loud warning -- or raises when params.pretrained is True."""
+    import warnings
     import torchvision.models as tvm
     fn = getattr(tvm, ctor)
-    if pretrained is not False:
-        try:
-            w = tvm.get_model_weights(ctor).DEFAULT
-            cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
-            if pretrained is True or os.path.isfile(cached):
-                return fn(weights=w)
-        except Exception as e:
-            print("bts_b200: pretrained %s weights unavailable (%s); using random init" % (ctor, type(e).__name__))
-    return fn(weights=None)
+    if pretrained is False or (pretrained is None and os.environ.get("BTS_B200_PRETRAINED", "1") == "0"):
+        return fn(weights=None)
+    try:
+        return fn(weights=tvm.get_model_weights(ctor).IMAGENET1K_V1)
+    except Exception as e:
+        if pretrained is True:
+            raise
+        msg = ("bts_b200: ImageNet (IMAGENET1K_V1) weights for %s could not be loaded or downloaded (%s: %s) -- the "
+               "encoder is RANDOMLY INITIALISED, unlike the reference (pytorch/bts.py:274-298). Put the checkpoint into "
+               "%s or pass params.pretrained=False to silence this." %
+               (ctor, type(e).__name__, e, os.path.join(torch.hub.get_dir(), "checkpoints")))
+        warnings.warn(msg, RuntimeWarning, stacklevel=2)
+        print("WARNING: " + msg)
+        return fn(weights=None)
 
 
 class encoder(nn.Module):
     """reference pytorch/bts.py:268-320.  The backbone modules (and therefore parameter names, which
     bts_main.set_misc freezes by substring, bts_main.py:222-247) are torchvision's, as in the reference.
-    params.pretrained: None (default) = use cached ImageNet weights if present, True = force, False = random."""
+    params.pretrained: None (default, as the reference: ImageNet V1 weights, downloaded if needed; loud warning + random
+    init when offline), True = must load, False = random init."""
 
     def __init__(self, params):
         super().__init__()

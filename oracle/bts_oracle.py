@@ -207,7 +207,10 @@ ENCODERS = {
     "resnet101_bts": ("resnet101", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
     "resnext50_bts": ("resnext50_32x4d", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
     "resnext101_bts": ("resnext101_32x8d", False, ["relu", "layer1", "layer2", "layer3", "layer4"], [64, 256, 512, 1024, 2048]),
+    # pytorch/bts.py:297-301: no tap names, the skips are the outputs of the 2nd/4th/7th/11th/19th module of `.features`
+    "mobilenetv2_bts": ("mobilenet_v2", True, [], [16, 24, 32, 64, 1280]),
 }
+MOBILENET_TAPS = (2, 4, 7, 11, 19)
 
 
 def build_encoder(name):
@@ -221,14 +224,19 @@ def build_encoder(name):
 
 
 def encoder_forward(base_model, names, x):
-    """encoder.forward, pytorch/bts.py:305-320."""
+    """encoder.forward, pytorch/bts.py:305-320 (names == [] selects the MobileNetV2 index taps, :312-314)."""
     skips = []
+    i = 1
     for k, v in base_model._modules.items():
         if "fc" in k or "avgpool" in k:
             continue
         x = v(x)
-        if any(n in k for n in names):
+        if not names:
+            if i in MOBILENET_TAPS:
+                skips.append(x)
+        elif any(n in k for n in names):
             skips.append(x)
+        i += 1
     return skips
 
 

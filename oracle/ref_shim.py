@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference `pytorch/bts.py`.
 
-Only usable where /root/reference exists (the build container).  It does not
-travel to the GPU box; nothing under tests -m gpu, smoke() or bench.py imports it.
-It is used by oracle/make_golden.py to generate tests/golden/*.npz and by the
-CPU tests that pin oracle/bts_oracle.py against the real reference.
+Where /root/reference exists (the build container) the file is loaded from there; `make -C oracle` also copies it,
+unmodified, into the git-ignored oracle/_ref/ so that it travels to the GPU box with the working tree (never into
+git history).  Used by oracle/make_golden.py to generate tests/golden/*.npz, by the CPU tests that pin
+oracle/bts_oracle.py against the real reference, and by bench.py's reference legs (`--impl reference`,
+`cpu_baseline`, `gpu_baseline`) -- never by the product path.
 
 Two shims, source untouched:
   (1) torchvision backbone ctors are called with weights=None
@@ -17,14 +18,38 @@ import sys
 
 import torch
 
-REFERENCE_DIR = os.environ.get("BTS_REFERENCE_DIR", "/root/reference/pytorch")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _reference_dir():
+    for d in (os.environ.get("BTS_REFERENCE_DIR"), "/root/reference/pytorch", os.path.join(_HERE, "_ref")):
+        if d and os.path.isfile(os.path.join(d, "bts.py")):
+            return d
+    return None
+
+
+REFERENCE_DIR = _reference_dir()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_DIR, "bts.py"))
+    return REFERENCE_DIR is not None
 
 
 _cached = None
+
+
+class cuda_is_identity:
+    """Context: Tensor.cuda() is the identity -- lets the reference's LPG (which calls .cuda() inside forward,
+    pytorch/bts.py:140,143) run on the CPU of a box that does have a GPU (bench.py's CPU reference arm)."""
+
+    def __enter__(self):
+        self.saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self.saved
+        return False
 
 
 def load_reference():
@@ -33,7 +58,7 @@ def load_reference():
     if _cached is not None:
         return _cached
     if not reference_available():
-        raise FileNotFoundError("reference not mounted at %s" % REFERENCE_DIR)
+        raise FileNotFoundError("reference not found (neither /root/reference/pytorch nor oracle/_ref)")
     import torchvision.models as tvm
 
     for name in ("densenet121", "densenet161", "resnet50", "resnet101",

@@ -11,6 +11,9 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# offline test boxes: random-init encoders without the download attempt + warning (the product default follows the
+# reference: ImageNet V1 weights, see bts_b200.model._load_backbone)
+os.environ.setdefault("BTS_B200_PRETRAINED", "0")
 
 
 def pytest_configure(config):

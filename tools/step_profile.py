@@ -11,7 +11,7 @@ B = int(os.environ.get("B", "16"))
 p = types.SimpleNamespace(encoder="densenet161_bts", max_depth=80.0, dataset="kitti", bts_size=512, pretrained=False)
 model = bts.BtsModel(p); model.train(); model.decoder.apply(bts.weights_init_xavier); bench.freeze_like_set_misc(model); model.to(dev)
 opt = bench.make_optimizer(model, torch); crit = bts.silog_loss(0.85)
-img, focal, gt = bench.synth_batch(B, 1, dev)
+img, focal, gt = bench.synth_batch(bench.CONFIGS["K16"], B, 1, dev)
 def step():
     opt.zero_grad()
     out = model(img, focal)
