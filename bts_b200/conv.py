@@ -54,8 +54,19 @@ def trace_report():
 _pack_cache = {}   # id(weight) -> (weakref, version, data_ptr, transpose) -> packed tensor
 
 
-def pack_weights(weight, transpose_flip=False):
-    """(Cout,Cin,KH,KW) fp32 parameter -> packed operator.  Cached on the tensor's version counter."""
+def invalidate_packed():
+    """Drops every cached packed operator.  The cache is keyed on the parameter's version counter, which in-place writes
+    through `.data` (apex / multi-tensor optimizers, manual EMA swaps, some checkpoint loaders) do not bump: call this
+    after such a write (torch.optim.* and load_state_dict bump the counter and need nothing)."""
+    _pack_cache.clear()
+
+
+def group_window(width, cpg):
+    return _lib.lib().bts_conv_group_window(int(width), int(cpg))
+
+
+def pack_weights(weight, transpose_flip=False, groups=1):
+    """(Cout,Cin/groups,KH,KW) fp32 parameter -> packed operator.  Cached on the tensor's version counter."""
     _need_cuda(weight)
     key = (id(weight), bool(transpose_flip))
     ent = _pack_cache.get(key)
@@ -67,12 +78,20 @@ def pack_weights(weight, transpose_flip=False):
     Cout, Cin, KH, KW = w.shape
     rows, kch = (Cin, Cout) if transpose_flip else (Cout, Cin)
     L = _lib.lib()
-    n = L.bts_conv_packed_floats(rows, kch, KH, KW)
-    packed = torch.empty(n, device=w.device, dtype=torch.float32)
     s = w.stride()
-    with torch.cuda.device(w.device):
-        _lib.check(L.bts_conv_pack_weights(_ptr(w), s[0], s[1], s[2], s[3], Cout, Cin, KH, KW, int(transpose_flip),
-                                           _ptr(packed), _stream()), "bts_conv_pack_weights")
+    if groups > 1:
+        if not group_window(Cout, Cin):
+            raise ValueError("grouped conv %s with %d groups is not supported by the block-diagonal engine path" % (tuple(w.shape), groups))
+        packed = torch.empty(L.bts_conv_packed_floats_grouped(Cout, Cin, KH, KW), device=w.device, dtype=torch.float32)
+        with torch.cuda.device(w.device):
+            _lib.check(L.bts_conv_pack_weights_grouped(_ptr(w), s[0], s[1], s[2], s[3], Cout, Cin, KH, KW,
+                                                       int(transpose_flip), _ptr(packed), _stream()),
+                       "bts_conv_pack_weights_grouped")
+    else:
+        packed = torch.empty(L.bts_conv_packed_floats(rows, kch, KH, KW), device=w.device, dtype=torch.float32)
+        with torch.cuda.device(w.device):
+            _lib.check(L.bts_conv_pack_weights(_ptr(w), s[0], s[1], s[2], s[3], Cout, Cin, KH, KW, int(transpose_flip),
+                                               _ptr(packed), _stream()), "bts_conv_pack_weights")
     _lib.count()
     _pack_cache[key] = (weakref.ref(weight), weight._version, w.data_ptr(), packed)
     if len(_pack_cache) > 4096:
@@ -97,26 +116,41 @@ def _nhwc_view(x):
 
 def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_shift=None, pre_relu=False,
               upsample2=False, act=None, out=None, precision=0, packed=None, cout=None, transpose_flip=False,
-              stats=None):
+              stats=None, groups=1, zero_stuff_out=None):
     """Runs the engine.  x: (B,Cin,Hs,Ws) NHWC-in-memory fp32 CUDA.  Returns (B,Cout,Hout,Wout) channels_last.
     `out` may be a pre-allocated channels_last tensor or a channel slice of one (concat-free writes).
     `stats`: a ZEROED fp64 [2, Cout] tensor that receives per-channel (sum, sum of squares) of the output, reduced in the
-    conv epilogue (Cout <= 256) -- the BatchNorm batch statistics of the tensor being produced."""
+    conv epilogue (Cout <= 256) -- the BatchNorm batch statistics of the tensor being produced.
+    `groups` > 1: block-diagonal operator (ResNeXt 3x3).  `zero_stuff_out=(H,W)`: x is the gradient of a stride-2 layer
+    whose input was HxW -- the source is read as its zero-stuffed x2 expansion (use with transpose_flip, stride 1)."""
     _need_cuda(x, weight)
     if x.dtype != torch.float32:
         raise TypeError("conv2d_tc computes in fp32 (3xTF32 on tcgen05); got %s" % x.dtype)
     x, xs = _nhwc_view(x)
     B, Cin, Hs, Ws = x.shape
     Co, Ci, KH, KW = weight.shape
-    if transpose_flip:
+    kwin = 0
+    if groups > 1:
+        kwin = group_window(Co, Ci)
+        if not kwin:
+            raise ValueError("unsupported grouped conv %s" % (tuple(weight.shape),))
+        Ci = Co                              # block diagonal: both sides carry the full width
+    elif transpose_flip:
         Co, Ci = Ci, Co
     if Ci != Cin:
         raise ValueError("weight expects %d input channels, got %d" % (Ci, Cin))
     if packed is None:
-        packed = pack_weights(weight, transpose_flip)
-    Hin, Win = (2 * Hs, 2 * Ws) if upsample2 else (Hs, Ws)
-    Hout = (Hin + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
-    Wout = (Win + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+        packed = pack_weights(weight, transpose_flip, groups)
+    if zero_stuff_out is not None:
+        mode = 2
+        Hout, Wout = int(zero_stuff_out[0]), int(zero_stuff_out[1])
+        if stride != 1 or upsample2:
+            raise ValueError("zero_stuff_out needs stride 1 and no up-sample")
+    else:
+        mode = 1 if upsample2 else 0
+        Hin, Win = (2 * Hs, 2 * Ws) if upsample2 else (Hs, Ws)
+        Hout = (Hin + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+        Wout = (Win + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
     if out is None:
         out = torch.empty((B, Co, Hout, Wout), device=x.device, dtype=torch.float32,
                           memory_format=torch.channels_last)
@@ -130,24 +164,49 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
     if pre_scale is not None:
         pre_scale = pre_scale.contiguous()
         pre_shift = pre_shift.contiguous()
+    if stats is not None and (stats.dtype != torch.float64 or tuple(stats.shape) != (2, Co) or not stats.is_contiguous()):
+        raise ValueError("stats must be a contiguous fp64 [2, Cout] tensor")
     with torch.cuda.device(x.device):
-        if stats is None:
-            call = lambda: _lib.lib().bts_conv_fwd(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride, padding,
-                                                   dilation, _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift),
-                                                   int(pre_relu), _ptr(out), os_, ACT[act], int(precision), _stream())
-        else:
-            if stats.dtype != torch.float64 or tuple(stats.shape) != (2, Co) or not stats.is_contiguous():
-                raise ValueError("stats must be a contiguous fp64 [2, Cout] tensor")
-            call = lambda: _lib.lib().bts_conv_fwd_stats(_ptr(x), xs, B, Hs, Ws, int(upsample2), Cin, KH, KW, stride,
-                                                         padding, dilation, _ptr(packed), Co, _ptr(pre_scale),
-                                                         _ptr(pre_shift), int(pre_relu), _ptr(out), os_, ACT[act],
-                                                         int(precision), _ptr(stats[0]), _ptr(stats[1]), _stream())
+        call = lambda: _lib.lib().bts_conv_fwd_ex(_ptr(x), xs, B, Hs, Ws, mode, Hout if mode == 2 else 0,
+                                                  Wout if mode == 2 else 0, kwin, Cin, KH, KW, stride, padding, dilation,
+                                                  _ptr(packed), Co, _ptr(pre_scale), _ptr(pre_shift), int(pre_relu),
+                                                  _ptr(out), os_, ACT[act], int(precision),
+                                                  _ptr(stats[0]) if stats is not None else None,
+                                                  _ptr(stats[1]) if stats is not None else None, _stream())
         rc = _traced("dgrad" if transpose_flip else "fwd",
-                     "%dx%dx%d %d->%d k%d d%d s%d%s" % (B, Hs, Ws, Cin, Co, KH, dilation, stride, " up" if upsample2 else ""),
-                     call, 2.0 * B * Hout * Wout * Co * Cin * KH * KW)
-    _lib.check(rc, "bts_conv_fwd")
+                     "%dx%dx%d %d->%d k%d d%d s%d%s%s" % (B, Hs, Ws, Cin, Co, KH, dilation, stride,
+                                                         " up" if upsample2 else (" zs" if mode == 2 else ""),
+                                                         " g%d" % groups if groups > 1 else ""),
+                     call, 2.0 * B * Hout * Wout * Co * (Cin // groups) * KH * KW / (4.0 if mode == 2 else 1.0))
+    _lib.check(rc, "bts_conv_fwd_ex")
     _lib.count()
     return out
+
+
+def wgrad_grouped_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=1, precision=0):
+    """dW of a grouped (block-diagonal) 3x3 conv: weight (width, cpg, KH, KW)"""
+    _need_cuda(x, gy)
+    x, xs = _nhwc_view(x)
+    gy, gs = _nhwc_view(gy)
+    B, width, Hs, Ws = x.shape
+    _, cpg, KH, KW = weight_shape
+    L = _lib.lib()
+    split = ctypes.c_int(0)
+    wsf = ctypes.c_longlong(0)
+    _lib.check(L.bts_conv_wgrad_grouped_plan(B, gy.shape[2], gy.shape[3], width, cpg, KH, KW, ctypes.byref(split),
+                                             ctypes.byref(wsf)), "bts_conv_wgrad_grouped_plan")
+    ws = torch.empty(wsf.value, device=x.device, dtype=torch.float32)
+    gw = torch.empty_strided(tuple(weight_shape), tuple(weight_strides), device=x.device, dtype=torch.float32)
+    s = weight_strides
+    with torch.cuda.device(x.device):
+        rc = _traced("wgrad", "%dx%dx%d %d->%d k%d d%d s%d g%d" % (B, Hs, Ws, width, width, KH, dilation, stride, width // cpg),
+                     lambda: L.bts_conv_wgrad_grouped(_ptr(x), xs, B, Hs, Ws, width, cpg, KH, KW, stride, padding, dilation,
+                                                      _ptr(gy), gs, _ptr(ws), split.value, _ptr(gw), s[0], s[1], s[2], s[3],
+                                                      int(precision), _stream()),
+                     2.0 * B * gy.shape[2] * gy.shape[3] * width * cpg * KH * KW)
+    _lib.check(rc, "bts_conv_wgrad_grouped")
+    _lib.count(2)
+    return gw
 
 
 def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=1, pre_scale=None, pre_shift=None,
@@ -174,7 +233,7 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
         return gw
     split = ctypes.c_int(0)
     wsf = ctypes.c_longlong(0)
-    _lib.check(L.bts_conv_wgrad_plan(B, gy.shape[2], gy.shape[3], Cin, Cout, KH, KW, ctypes.byref(split), ctypes.byref(wsf)),
+    _lib.check(L.bts_conv_wgrad_plan(B, gy.shape[2], gy.shape[3], Cin, Cout, KH, KW, stride, ctypes.byref(split), ctypes.byref(wsf)),
                "bts_conv_wgrad_plan")
     ws = torch.empty(wsf.value, device=x.device, dtype=torch.float32)
     gw = torch.empty_strided(tuple(weight_shape), tuple(weight_strides), device=x.device, dtype=torch.float32)
@@ -196,34 +255,42 @@ def wgrad_tc(x, gy, weight_shape, weight_strides, stride=1, padding=0, dilation=
 
 class _ConvTC(torch.autograd.Function):
     """Plain convolution (no fused pre/post ops) with autograd, all three GEMMs on the tcgen05 engine: forward,
-    dgrad (the same kernel over the transposed, tap-flipped packed operator) and wgrad (MN-major operands)."""
+    dgrad (the same kernel over the transposed, tap-flipped packed operator; a stride-2 layer's dgrad reads dY as its
+    zero-stuffed expansion) and wgrad (MN-major operands).  groups > 1: block-diagonal operator (ResNeXt)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, padding, dilation):
-        y = conv2d_tc(x, weight, stride, padding, dilation)
+    def forward(ctx, x, weight, stride, padding, dilation, groups):
+        y = conv2d_tc(x, weight, stride, padding, dilation, groups=groups)
         ctx.save_for_backward(x, weight)
-        ctx.cfg = (stride, padding, dilation)
+        ctx.cfg = (stride, padding, dilation, groups)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
-        stride, padding, dilation = ctx.cfg
+        stride, padding, dilation, groups = ctx.cfg
         gx = gw = None
         KH = weight.shape[2]
         if ctx.needs_input_grad[0]:
+            padT = dilation * (KH - 1) - padding
             if stride == 1:
-                gx = conv2d_tc(gy, weight, 1, dilation * (KH - 1) - padding, dilation, transpose_flip=True)
+                gx = conv2d_tc(gy, weight, 1, padT, dilation, transpose_flip=True, groups=groups)
+            elif stride == 2 and padT >= 0:
+                gx = conv2d_tc(gy, weight, 1, padT, dilation, transpose_flip=True, groups=groups,
+                               zero_stuff_out=(x.shape[2], x.shape[3]))
             else:
-                gx = torch.ops.aten.convolution_backward(gy, x, weight, None, [stride] * 2, [padding] * 2, [dilation] * 2,
-                                                         False, [0, 0], 1, [True, False, False])[0]
+                raise NotImplementedError("conv dgrad on the engine: stride %d / padding %d not covered (BTS encoders use "
+                                          "stride 1 and 2 only)" % (stride, padding))
         if ctx.needs_input_grad[1]:
-            gw = wgrad_tc(x, gy, weight.shape, weight.stride(), stride, padding, dilation)
-        return gx, gw, None, None, None
+            if groups > 1:
+                gw = wgrad_grouped_tc(x, gy, weight.shape, weight.stride(), stride, padding, dilation)
+            else:
+                gw = wgrad_tc(x, gy, weight.shape, weight.stride(), stride, padding, dilation)
+        return gx, gw, None, None, None, None
 
 
-def conv2d(x, weight, stride=1, padding=0, dilation=1):
-    return _ConvTC.apply(x, weight, stride, padding, dilation)
+def conv2d(x, weight, stride=1, padding=0, dilation=1, groups=1):
+    return _ConvTC.apply(x, weight, stride, padding, dilation, groups)
 
 
 # ---------------------------------------------------------------------------- single-output-channel heads

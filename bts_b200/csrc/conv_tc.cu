@@ -55,8 +55,11 @@ struct ConvParams {
     const float *x;          // NHWC source, pixel stride xs floats
     long long xs;
     int B, Hs, Ws;           // source dims (before the optional x2 up-sample)
-    int up;                  // 1: nearest x2 up-sample folded in (conv sees 2Hs x 2Ws)
-    int Cin;
+    int up;                  // 1: nearest x2 up-sample folded in (conv sees 2Hs x 2Ws); 2: zero-stuffed x2 (the dgrad of a
+                             //    stride-2 convolution: only even coordinates of the Hv x Wv virtual source are live)
+    int Hv, Wv;              // virtual source dims seen by the conv (= Hs,Ws | 2Hs,2Ws | the stride-2 layer's input size)
+    int Cin;                 // K channels per tap of ONE n-tile (grouped: the channel window, else all input channels)
+    int kwin;                // grouped / block-diagonal: n-tile nt reads input channels [nt*kwin, nt*kwin + Cin); 0 = dense
     int KH, KW, stride, pad, dil;
     const float *wpack;      // packed weights (see pack kernel)
     int n_tile, n_tiles, Cout;
@@ -94,9 +97,11 @@ using namespace tc;
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
                                                            long long s_kh, long long s_kw, int Cout, int Cin, int KH,
                                                            int KW, int transpose_flip, float *__restrict__ wpack,
-                                                           int n_tile, int n_tiles) {
+                                                           int n_tile, int n_tiles, int kwin, int cpg) {
+    // grouped (kwin > 0): Cin == Cout == total width, w is (width, cpg, KH, KW); rows = all channels, the K channels of
+    // n-tile nt are the window [nt*kwin, (nt+1)*kwin) and entries outside the row's group are zero (block diagonal)
     const int Nrows = transpose_flip ? Cin : Cout;    // GEMM N
-    const int Kch = transpose_flip ? Cout : Cin;      // GEMM K channels per tap
+    const int Kch = kwin ? kwin : (transpose_flip ? Cout : Cin);      // GEMM K channels per tap
     const int CQ = (Kch + 3) / 4;
     const int taps = KH * KW;
     const int KB = (taps * CQ + 7) / 8;
@@ -116,13 +121,21 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
         if (row < Nrows && tap < taps && ch < Kch) {
             int kh = tap / KW, kw = tap % KW;
             long long off;
+            bool live = true;
+            int kc = ch, rr = row;            // K channel / row index into w's (co, ci) axes
+            if (kwin) {
+                const int kglob = nt * kwin + ch;                 // global channel on the K side
+                live = (kglob / cpg) == (row / cpg);
+                if (transpose_flip) { kc = kglob; rr = row % cpg; }   // w[co = kglob][ci_local = row % cpg]
+                else { kc = kglob % cpg; }                            // w[co = row][ci_local = kglob % cpg]
+            }
             if (transpose_flip) {
                 kh = KH - 1 - kh; kw = KW - 1 - kw;
-                off = (long long)ch * s_co + (long long)row * s_ci + kh * s_kh + kw * s_kw;
+                off = (long long)kc * s_co + (long long)rr * s_ci + kh * s_kh + kw * s_kw;
             } else {
-                off = (long long)row * s_co + (long long)ch * s_ci + kh * s_kh + kw * s_kw;
+                off = (long long)rr * s_co + (long long)kc * s_ci + kh * s_kh + kw * s_kw;
             }
-            val = w[off];
+            if (live) val = w[off];
         }
         const float hi = rna_tf32(val);
         const float lo = rna_tf32(val - hi);
@@ -154,7 +167,7 @@ constexpr int STAT_BYTES = 2 * MAX_N * 4;   // per-CTA fp32 partial sums of the 
 //   * the per-tile pixel decode uses multiply-shift division by host-precomputed constants (FastDiv);
 //   * long waits (epilogue on the accumulator, weight loader on a free stage) back off with nanosleep so the spinning
 //     warps stop competing with the producers for issue slots.
-template <int PRE, bool UP, bool VEC>
+template <int PRE, int UP, bool VEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const int t = pt & 127;
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7  (row & 7 == r0 & 7 for all of them)
-        const int Hin = UP ? 2 * p.Hs : p.Hs, Win = UP ? 2 * p.Ws : p.Ws;
+        const int Hin = p.Hv, Win = p.Wv;
         const int xs = (int)p.xs;                  // host guarantees the source has < 2^31 elements
         const int KW = p.KW, dil = p.dil, Cin = p.Cin, Ws = p.Ws;
         const int taps = p.KH * p.KW;
@@ -310,6 +323,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntiles);
             const uint32_t m_base = m_tile * BLOCK_M + (uint32_t)r0;
+            const int cwin = (tile - (int)m_tile * p.n_tiles) * p.kwin;     // first input channel of this n-tile's window
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint32_t m = m_base + 16u * i;
@@ -320,7 +334,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     const int y = (int)(q - b * (uint32_t)p.Hout);
                     oy[i] = y * p.stride - p.pad;
                     ox[i] = x * p.stride - p.pad;
-                    rowoff[i] = (int)b * p.Hs * Ws * xs + (UP ? 0 : (oy[i] * Ws + ox[i]) * xs);
+                    rowoff[i] = (int)b * p.Hs * Ws * xs + (UP ? 0 : (oy[i] * Ws + ox[i]) * xs) + cwin;
                 } else {
                     oy[i] = ox[i] = -0x40000000;   // never in bounds
                     rowoff[i] = 0;
@@ -343,7 +357,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int yy = oy[i] + dy, xx = ox[i] + dx;
-                const bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                if (UP == 2) ok = ok && (((yy | xx) & 1) == 0);          // zero-stuffed source: odd coordinates are zeros
                 mk |= (ok ? 1u : 0u) << i;
                 int off;
                 if (UP) off = rowoff[i] + ((yy >> 1) * Ws + (xx >> 1)) * xs + tapoff;
@@ -566,12 +581,53 @@ extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s
     const long long cap = (long long)bts_num_sms() * 16;
     if (grid > cap) grid = cap;
     pack_weights_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW,
-                                                                    transpose_flip, wpack, n_tile, n_tiles);
+                                                                    transpose_flip, wpack, n_tile, n_tiles, 0, 1);
     BTS_LAUNCH_CHECK();
     return 0;
 }
 
-static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
+// Grouped convolution whose groups tile a 128-wide diagonal block (ResNeXt 3x3: width % kwin == 0, kwin % cpg == 0):
+// w is (width, cpg, KH, KW); the packed operator has width/kwin n-tiles of kwin rows, each over the K window of kwin
+// channels -- zeros outside the row's group.  Run with bts_conv_fwd_ex(kwin = bts_conv_group_window(width, cpg)).
+extern "C" int bts_conv_group_window(int width, int cpg) {
+    if (width < 1 || cpg < 1 || width % cpg) return 0;
+    int k = 128;
+    if (width % k || k % cpg) {
+        // narrower windows for widths that are not multiples of 128: the largest multiple of lcm(16, cpg) dividing width
+        k = 0;
+        for (int c = 16; c <= 256 && c <= width; c += 16)
+            if (width % c == 0 && c % cpg == 0) k = c;
+    }
+    return k;
+}
+
+extern "C" long long bts_conv_packed_floats_grouped(int width, int cpg, int KH, int KW) {
+    const int kwin = bts_conv_group_window(width, cpg);
+    if (!kwin) return 0;
+    const int CQ = kwin / 4;
+    const int KB = (KH * KW * CQ + 7) / 8;
+    return (long long)(width / kwin) * KB * 2 * kwin * 32;
+}
+
+extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
+                                             int width, int cpg, int KH, int KW, int transpose_flip, float *wpack,
+                                             void *stream) {
+    if (!w || !wpack || KH < 1 || KW < 1) return BTS_EINVAL;
+    const int kwin = bts_conv_group_window(width, cpg);
+    if (!kwin) return BTS_EINVAL;
+    if (!bts_aligned16(wpack)) return BTS_EALIGN;
+    const long long total = bts_conv_packed_floats_grouped(width, cpg, KH, KW) / 2;
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    pack_weights_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(w, s_co, s_ci, s_kh, s_kw, width, width, KH, KW,
+                                                                    transpose_flip, wpack, kwin, width / kwin, kwin, cpg);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int out_h,
+                         int out_w, int kwin, int Cin,
                          int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                          const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
                          long long out_pixel_stride, int act, int precision, double *stat_sum, double *stat_sumsq,
@@ -582,14 +638,19 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BTS_EINVAL;
     if (pre_scale && Cin > MAX_CIN_SMEM) return BTS_EINVAL;
     if (act < 0 || act > 2 || precision < 0 || precision > 1) return BTS_EINVAL;
+    if (upsample2 < 0 || upsample2 > 2 || kwin < 0) return BTS_EINVAL;
+    if (upsample2 == 2 && (stride != 1 || out_h < 1 || out_w < 1)) return BTS_EINVAL;
+    if (kwin && (pre_scale || Cin % kwin || Cout % kwin)) return BTS_EINVAL;   // window = n-tile width; no pre-op on grouped convs
     if (!bts_aligned16(wpack)) return BTS_EALIGN;
     if (B == 0) return 0;
     if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;   // 32-bit element offsets
     ConvParams p;
-    p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = upsample2 ? 1 : 0; p.Cin = Cin;
+    p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = upsample2; p.Cin = kwin ? kwin : Cin;
+    p.kwin = kwin;
     p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = dil;
     p.wpack = wpack; p.Cout = Cout;
-    p.n_tile = bts_conv_n_tile(Cout);
+    p.n_tile = kwin ? kwin : bts_conv_n_tile(Cout);
+    if (kwin && (kwin % 16 || kwin > MAX_N)) return BTS_EINVAL;
     p.n_tiles = (Cout + p.n_tile - 1) / p.n_tile;
     p.pre_scale = pre_scale; p.pre_shift = pre_shift; p.pre_relu = pre_relu ? 1 : 0;
     p.out = out; p.os = out_pixel_stride; p.act = act; p.precision = precision;
@@ -597,12 +658,13 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     if ((stat_sum == nullptr) != (stat_sumsq == nullptr)) return BTS_EINVAL;
     if (stat_sum && (p.n_tiles != 1 || act != 0)) return BTS_EINVAL;   // epilogue statistics: one N tile (Cout <= 256), no activation
     const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
-    p.Hout = (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
-    p.Wout = (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    p.Hv = Hin; p.Wv = Win;      // mode 2: live source coordinates are the even ones below 2Hs x 2Ws, zeros everywhere else
+    p.Hout = p.up == 2 ? out_h : (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    p.Wout = p.up == 2 ? out_w : (Win + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     if (p.Hout < 1 || p.Wout < 1) return BTS_EINVAL;
     p.M = (long long)B * p.Hout * p.Wout;
-    p.KC = (Cin + 31) / 32;
-    p.CQ = (Cin + 3) / 4;
+    p.KC = (p.Cin + 31) / 32;
+    p.CQ = (p.Cin + 3) / 4;
     p.KB = (KH * KW * p.CQ + 7) / 8;
     p.fd_cq = make_fastdiv((uint32_t)p.CQ);
     p.fd_kw = make_fastdiv((uint32_t)KW);
@@ -640,8 +702,9 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                  \
     do {                                                      \
-        if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true); else BTS_LAUNCH(PRE, true, false); }   \
-        else { if (vec) BTS_LAUNCH(PRE, false, true); else BTS_LAUNCH(PRE, false, false); }      \
+        if (p.up == 2) { if (vec) BTS_LAUNCH(PRE, 2, true); else BTS_LAUNCH(PRE, 2, false); }    \
+        else if (p.up) { if (vec) BTS_LAUNCH(PRE, 1, true); else BTS_LAUNCH(PRE, 1, false); }    \
+        else { if (vec) BTS_LAUNCH(PRE, 0, true); else BTS_LAUNCH(PRE, 0, false); }              \
     } while (0)
     switch (pre) {
         case 0: BTS_DISPATCH_UV(0); break;
@@ -659,8 +722,8 @@ extern "C" int bts_conv_fwd(const float *x, long long x_pixel_stride, int B, int
                             int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                             const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
                             long long out_pixel_stride, int act, int precision, void *stream) {
-    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2, Cin, KH, KW, stride, pad, dil, wpack, Cout, pre_scale,
-                         pre_shift, pre_relu, out, out_pixel_stride, act, precision, nullptr, nullptr, stream);
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2 ? 1 : 0, 0, 0, 0, Cin, KH, KW, stride, pad, dil, wpack, Cout,
+                         pre_scale, pre_shift, pre_relu, out, out_pixel_stride, act, precision, nullptr, nullptr, stream);
 }
 
 extern "C" int bts_conv_fwd_stats(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
@@ -669,6 +732,24 @@ extern "C" int bts_conv_fwd_stats(const float *x, long long x_pixel_stride, int 
                                   long long out_pixel_stride, int act, int precision, double *stat_sum,
                                   double *stat_sumsq, void *stream) {
     if (!stat_sum || !stat_sumsq) return BTS_EINVAL;
-    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2, Cin, KH, KW, stride, pad, dil, wpack, Cout, pre_scale,
-                         pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq, stream);
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, upsample2 ? 1 : 0, 0, 0, 0, Cin, KH, KW, stride, pad, dil, wpack, Cout,
+                         pre_scale, pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq, stream);
+}
+
+// General entry point: everything bts_conv_fwd does, plus
+//   source_mode 2: the source is the zero-stuffed x2 expansion of x (value at (2i,2j) = x[i,j], zeros elsewhere) and the
+//       output has the given out_h x out_w -- with the transposed, tap-flipped packed operator and pad' = dil*(K-1) - pad
+//       this is the input gradient of a STRIDE-2 convolution whose input was out_h x out_w (ResNet / ResNeXt stages,
+//       pytorch/bts.py:282-296 via torchvision); call with stride = 1;
+//   kwin > 0: block-diagonal ("grouped") operator: output channels [nt*kwin, (nt+1)*kwin) only see input channels
+//       [nt*kwin, (nt+1)*kwin) (ResNeXt 3x3 convs, 32 groups: groups are packed kwin/cpg to a 128-wide diagonal block,
+//       see bts_conv_pack_weights_grouped); Cin and Cout are the layer's total channel counts.
+extern "C" int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int source_mode, int out_h,
+                               int out_w, int kwin, int Cin, int KH, int KW, int stride, int pad, int dil,
+                               const float *wpack, int Cout, const float *pre_scale, const float *pre_shift, int pre_relu,
+                               float *out, long long out_pixel_stride, int act, int precision, double *stat_sum,
+                               double *stat_sumsq, void *stream) {
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, source_mode, out_h, out_w, kwin, Cin, KH, KW, stride, pad, dil, wpack,
+                         Cout, pre_scale, pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq,
+                         stream);
 }

@@ -11,6 +11,8 @@
 //   bts_avgpool2 / _bwd  2x2 stride-2 average pool (DenseNet transitions) and its backward
 // Each thread moves 16 bytes; a warp covers 512 contiguous bytes of a pixel row group -> fully coalesced 128-bit
 // transactions whenever C % 4 == 0 and the strides / bases are 16-byte aligned (scalar tail path otherwise).
+#include <cmath>
+
 #include "common.cuh"
 
 namespace {
@@ -197,6 +199,116 @@ __global__ void __launch_bounds__(TPB) avgpool2_kernel(const float *__restrict__
     }
 }
 
+// ResNet / ResNeXt bottleneck tail (torchvision Bottleneck.forward: out = relu(bn3(conv3) + identity)):
+//   out = max(x*scale + shift + res, 0)
+__global__ void __launch_bounds__(TPB) bn_add_relu_kernel(const float *__restrict__ x, long long xs, long long M, int C,
+                                                          const float *__restrict__ scale, const float *__restrict__ shift,
+                                                          const float *__restrict__ res, long long rs,
+                                                          float *__restrict__ out, long long os) {
+    const int cq = (C + 3) >> 2;
+    const long long total = M * cq;
+    const bool vec = ((C & 3) == 0) && ((xs & 3) == 0) && ((os & 3) == 0) && ((rs & 3) == 0) && al16(x) && al16(out) && al16(res) &&
+                     al16(scale) && al16(shift);
+    for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < total; idx += (long long)gridDim.x * TPB) {
+        const long long m = idx / cq;
+        const int c = (int)(idx - m * cq) * 4;
+        if (vec) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(x + m * xs + c));
+            const float4 r0 = __ldg(reinterpret_cast<const float4 *>(res + m * rs + c));
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(scale + c));
+            const float4 h = __ldg(reinterpret_cast<const float4 *>(shift + c));
+            float4 r = make_float4(fmaf(q.x, s.x, h.x) + r0.x, fmaf(q.y, s.y, h.y) + r0.y, fmaf(q.z, s.z, h.z) + r0.z,
+                                   fmaf(q.w, s.w, h.w) + r0.w);
+            r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+            *reinterpret_cast<float4 *>(out + m * os + c) = r;
+        } else {
+            for (int e = 0; e < 4 && c + e < C; ++e)
+                out[m * os + c + e] = fmaxf(fmaf(x[m * xs + c + e], scale[c + e], shift[c + e]) + res[m * rs + c + e], 0.f);
+        }
+    }
+}
+
+// out = gy * (y > 0): backward of a ReLU expressed through its saved OUTPUT
+__global__ void __launch_bounds__(TPB) relu_bwd_kernel(const float *__restrict__ gy, long long gs, const float *__restrict__ y,
+                                                       long long ys, long long M, int C, float *__restrict__ out, long long os) {
+    const int cq = (C + 3) >> 2;
+    const long long total = M * cq;
+    const bool vec = ((C & 3) == 0) && ((gs & 3) == 0) && ((ys & 3) == 0) && ((os & 3) == 0) && al16(gy) && al16(y) && al16(out);
+    for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < total; idx += (long long)gridDim.x * TPB) {
+        const long long m = idx / cq;
+        const int c = (int)(idx - m * cq) * 4;
+        if (vec) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(gy + m * gs + c));
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(y + m * ys + c));
+            *reinterpret_cast<float4 *>(out + m * os + c) =
+                make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
+        } else {
+            for (int e = 0; e < 4 && c + e < C; ++e) out[m * os + c + e] = y[m * ys + c + e] > 0.f ? gy[m * gs + c + e] : 0.f;
+        }
+    }
+}
+
+// 3x3 / stride 2 / pad 1 max-pool of the encoder stems (torchvision densenet `pool0`, resnet `maxpool`), NHWC.
+// Forward also records which of the 9 window positions won (first maximum in row-major scan order, NaN propagates --
+// the tie rule of at::max_pool2d) so the backward is a deterministic gather: each input pixel looks at the <= 4 windows
+// that contain it.
+__global__ void __launch_bounds__(TPB) maxpool3s2_fwd_kernel(const float *__restrict__ x, long long xs, int B, int H, int W, int C,
+                                                             int Ho, int Wo, float *__restrict__ out, long long os,
+                                                             unsigned char *__restrict__ arg) {
+    const long long total = (long long)B * Ho * Wo * C;
+    for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < total; idx += (long long)gridDim.x * TPB) {
+        const int c = (int)(idx % C);
+        long long t = idx / C;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int b = (int)(t / Ho);
+        float best = -INFINITY;
+        int bi = 0;
+        bool first = true;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int y = 2 * oy - 1 + ky, xx = 2 * ox - 1 + kx;
+                if ((unsigned)y < (unsigned)H && (unsigned)xx < (unsigned)W) {
+                    const float v = __ldg(x + (((long long)b * H + y) * W + xx) * xs + c);
+                    if (first) { bi = ky * 3 + kx; first = false; }       // at::max_pool2d: index starts at the first valid tap
+                    if (v > best || v != v) { best = v; bi = ky * 3 + kx; }   // strict >: the first maximum wins; NaN propagates
+                }
+            }
+        out[(((long long)b * Ho + oy) * Wo + ox) * os + c] = best;
+        arg[idx] = (unsigned char)bi;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) maxpool3s2_bwd_kernel(const float *__restrict__ g, long long gs,
+                                                             const unsigned char *__restrict__ arg, int B, int H, int W, int C,
+                                                             int Ho, int Wo, float *__restrict__ gx, long long gxs) {
+    const long long total = (long long)B * H * W * C;
+    for (long long idx = (long long)blockIdx.x * TPB + threadIdx.x; idx < total; idx += (long long)gridDim.x * TPB) {
+        const int c = (int)(idx % C);
+        long long t = idx / C;
+        const int xx = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc = 0.f;
+        // windows (oy, ox) with 2*oy - 1 <= y <= 2*oy + 1
+        for (int oy = y >> 1; oy <= ((y + 1) >> 1); ++oy) {
+            if (oy >= Ho) continue;
+            const int ky = y - (2 * oy - 1);
+            for (int ox = xx >> 1; ox <= ((xx + 1) >> 1); ++ox) {
+                if (ox >= Wo) continue;
+                const int kx = xx - (2 * ox - 1);
+                const long long o = (((long long)b * Ho + oy) * Wo + ox);
+                if (arg[o * C + c] == ky * 3 + kx) acc += __ldg(g + o * gs + c);
+            }
+        }
+        gx[(((long long)b * H + y) * W + xx) * gxs + c] = acc;
+    }
+}
+
 }  // namespace
 
 extern "C" int bts_bn_apply(const float *x, long long x_pixel_stride, long long M, int C, const float *scale,
@@ -256,6 +368,45 @@ extern "C" int bts_avgpool2_bwd(const float *g, long long g_pixel_stride, int B,
     if (!g || !gx || B < 1 || Hout < 1 || Wout < 1 || C < 1) return BTS_EINVAL;
     avgpool2_kernel<true><<<stream_grid((long long)B * 4 * Hout * Wout * ((C + 3) / 4)), TPB, 0, (cudaStream_t)stream>>>(
         g, g_pixel_stride, B, Hout, Wout, C, gx, gx_pixel_stride);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_bn_add_relu(const float *x, long long x_pixel_stride, long long M, int C, const float *scale,
+                               const float *shift, const float *res, long long res_pixel_stride, float *out,
+                               long long out_pixel_stride, void *stream) {
+    if (!x || !scale || !shift || !res || !out || M < 1 || C < 1) return BTS_EINVAL;
+    bn_add_relu_kernel<<<stream_grid(M * ((C + 3) / 4)), TPB, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, M, C, scale, shift, res,
+                                                                                          res_pixel_stride, out, out_pixel_stride);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_relu_bwd(const float *gy, long long gy_pixel_stride, const float *y, long long y_pixel_stride, long long M,
+                            int C, float *out, long long out_pixel_stride, void *stream) {
+    if (!gy || !y || !out || M < 1 || C < 1) return BTS_EINVAL;
+    relu_bwd_kernel<<<stream_grid(M * ((C + 3) / 4)), TPB, 0, (cudaStream_t)stream>>>(gy, gy_pixel_stride, y, y_pixel_stride, M,
+                                                                                       C, out, out_pixel_stride);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_maxpool3s2_fwd(const float *x, long long x_pixel_stride, int B, int H, int W, int C, float *out,
+                                  long long out_pixel_stride, unsigned char *argmax, void *stream) {
+    if (!x || !out || !argmax || B < 1 || H < 1 || W < 1 || C < 1) return BTS_EINVAL;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    maxpool3s2_fwd_kernel<<<stream_grid((long long)B * Ho * Wo * C), TPB, 0, (cudaStream_t)stream>>>(
+        x, x_pixel_stride, B, H, W, C, Ho, Wo, out, out_pixel_stride, argmax);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int bts_maxpool3s2_bwd(const float *g, long long g_pixel_stride, const unsigned char *argmax, int B, int H, int W,
+                                  int C, float *gx, long long gx_pixel_stride, void *stream) {
+    if (!g || !gx || !argmax || B < 1 || H < 1 || W < 1 || C < 1) return BTS_EINVAL;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    maxpool3s2_bwd_kernel<<<stream_grid((long long)B * H * W * C), TPB, 0, (cudaStream_t)stream>>>(
+        g, g_pixel_stride, argmax, B, H, W, C, Ho, Wo, gx, gx_pixel_stride);
     BTS_LAUNCH_CHECK();
     return 0;
 }

@@ -37,7 +37,8 @@ struct WgradParams {
     const float *dy; long long dys;
     int Cout, Hout, Wout;
     int n_tile;
-    float *part;             // [splitK][taps][Cin][Cout]
+    int kwin;                // grouped (block-diagonal) layer: only the tiles ci_tile == nt exist, n_tile == kwin == 128
+    float *part;             // [splitK][taps][Cin][Cout]   (grouped: [splitK][taps][Cin][kwin])
     int splitK, kb_per_split, KBp;
     int M;
     int x_vec, dy_vec, precision;
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci_tile = blockIdx.x, nt = blockIdx.y;
+    const int nt = blockIdx.y;
+    const int ci_tile = p.kwin ? nt : blockIdx.x;
     const int tap = blockIdx.z / p.splitK, split = blockIdx.z % p.splitK;
     const int n_tile = p.n_tile;
     const int kb0 = split * p.kb_per_split;
@@ -358,7 +360,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         const int half = n_tile >> 1;
         const int col0 = grp * half;
         const int taps = p.KH * p.KW;
-        float *prow = p.part + (((long long)split * taps + tap) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + (long long)nt * n_tile;
+        float *prow = p.kwin ? p.part + (((long long)split * taps + tap) * p.Cin + (ci < p.Cin ? ci : 0)) * n_tile
+                             : p.part + (((long long)split * taps + tap) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + (long long)nt * n_tile;
         const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0);
         const int lo_col = ((n_tile + 31) >> 5) * 32;       // first accumulator column of the x_hi * dY_lo block
         for (int cc = 0; cc < half; cc += 8) {
@@ -413,6 +416,27 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
     }
 }
 
+// grouped layers: dW[co, ci_local, kh, kw] = sum_split part[split][tap][ci = (co / cpg) * cpg + ci_local][co % kwin]
+__global__ void __launch_bounds__(256) wgrad_reduce_grouped_kernel(const float *__restrict__ part, int splitK, int taps,
+                                                                   int width, int kwin, int cpg, int KW,
+                                                                   float *__restrict__ dw, long long s_co, long long s_ci,
+                                                                   long long s_kh, long long s_kw) {
+    const long long per = (long long)taps * width * kwin;          // one split of the partial buffer
+    const long long total = (long long)taps * width * cpg;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cl = (int)(idx % cpg);
+        const long long t = idx / cpg;
+        const int co = (int)(t % width);
+        const int tap = (int)(t / width);
+        const int ci = (co / cpg) * cpg + cl;
+        const long long src = ((long long)tap * width + ci) * kwin + (co % kwin);
+        float acc = 0.f;
+        for (int s = 0; s < splitK; ++s) acc += part[(long long)s * per + src];
+        dw[co * s_co + cl * s_ci + (tap / KW) * s_kh + (tap % KW) * s_kw] = acc;
+    }
+}
+
 }  // namespace
 
 // N tile of the wgrad kernels (their shared-memory plan holds <= 128 output channels per CTA)
@@ -438,10 +462,10 @@ int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int u
                       long long dys, int Cout, int Hout, int Wout, float *workspace, int splitK, int precision,
                       cudaStream_t st);
 
-extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int *splitK_out,
-                                   long long *workspace_floats) {
-    if (!splitK_out || !workspace_floats || B < 1 || Hout < 1 || Wout < 1 || Cin < 1 || Cout < 1) return BTS_EINVAL;
-    if (bts_wgrad2_eligible(Cout, KH, KW, 1, (long long)B * Hout * Wout)) {
+extern "C" int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int stride,
+                                   int *splitK_out, long long *workspace_floats) {
+    if (!splitK_out || !workspace_floats || B < 1 || Hout < 1 || Wout < 1 || Cin < 1 || Cout < 1 || stride < 1) return BTS_EINVAL;
+    if (bts_wgrad2_eligible(Cout, KH, KW, stride, (long long)B * Hout * Wout)) {
         int sp = 1;
         bts_wgrad2_plan(B, Hout, Wout, Cin, Cout, KH, KW, &sp);
         *splitK_out = sp;
@@ -494,6 +518,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL || M * dy_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;
     p.M = (int)M;
     p.n_tile = wgrad_n_tile(Cout);
+    p.kwin = 0;
     p.part = workspace; p.splitK = splitK;
     p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
     p.kb_per_split = (p.KBp + splitK - 1) / splitK;
@@ -559,6 +584,101 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     const long long cap = (long long)bts_num_sms() * 16;
     if (g > cap) g = cap;
     wgrad_reduce_kernel<<<(int)g, 256, 0, st>>>(workspace, splitK, taps, Cin, Cout, KW, dw, s_co, s_ci, s_kh, s_kw);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- grouped (block-diagonal) wgrad
+// ResNeXt 3x3 convs (pytorch/bts.py:291-296 via torchvision, 32 groups): x and dy carry `width` channels each, w is
+// (width, cpg, KH, KW).  Only the diagonal 128 x 128 channel blocks are computed (one CTA per block, tap and split),
+// the reduce kernel extracts every group's cpg x cpg sub-block.  Requires bts_conv_group_window(width, cpg) == 128.
+extern "C" int bts_conv_group_window(int width, int cpg);
+
+static long long wgrad_grouped_split(long long M, int width, int taps) {
+    const long long KBp = (M + BLOCK_KP - 1) / BLOCK_KP;
+    const long long tiles = (long long)(width / 128) * taps;
+    const int sms = bts_num_sms();
+    long long max_split = (KBp + 15) / 16;
+    if (max_split < 1) max_split = 1;
+    if (max_split > 64) max_split = 64;
+    long long split = 1;
+    double best = -1.0;
+    for (long long sp = 1; sp <= max_split; ++sp) {
+        const long long ctas = tiles * sp;
+        const long long waves = (ctas + sms - 1) / sms;
+        if (waves > 4 && sp > 1) break;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff >= best - 1e-9) { best = eff; split = sp; }
+    }
+    return split;
+}
+
+extern "C" int bts_conv_wgrad_grouped_plan(int B, int Hout, int Wout, int width, int cpg, int KH, int KW, int *splitK_out,
+                                           long long *workspace_floats) {
+    if (!splitK_out || !workspace_floats || B < 1 || Hout < 1 || Wout < 1 || KH < 1 || KW < 1) return BTS_EINVAL;
+    if (bts_conv_group_window(width, cpg) != 128) return BTS_EINVAL;
+    const long long split = wgrad_grouped_split((long long)B * Hout * Wout, width, KH * KW);
+    *splitK_out = (int)split;
+    *workspace_floats = split * KH * KW * (long long)width * 128;
+    return 0;
+}
+
+extern "C" int bts_conv_wgrad_grouped(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int width, int cpg,
+                                      int KH, int KW, int stride, int pad, int dil, const float *dy,
+                                      long long dy_pixel_stride, float *workspace, int splitK, float *dw, long long s_co,
+                                      long long s_ci, long long s_kh, long long s_kw, int precision, void *stream) {
+    if (!x || !dy || !workspace || !dw || B < 1 || Hs < 1 || Ws < 1 || KH < 1 || KW < 1 || stride < 1 || pad < 0 || dil < 1 ||
+        splitK < 1)
+        return BTS_EINVAL;
+    if (bts_conv_group_window(width, cpg) != 128) return BTS_EINVAL;
+    WgradParams p;
+    p.x = x; p.xs = x_pixel_stride; p.B = B; p.Hs = Hs; p.Ws = Ws; p.up = 0; p.Cin = width;
+    p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = dil;
+    p.pre_scale = nullptr; p.pre_shift = nullptr; p.pre_relu = 0;
+    p.dy = dy; p.dys = dy_pixel_stride; p.Cout = width;
+    p.Hout = (Hs + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    p.Wout = (Ws + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    const long long M = (long long)B * p.Hout * p.Wout;
+    if (p.Hout < 1 || p.Wout < 1 || M > 0x7ffffff0LL) return BTS_EINVAL;
+    if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL || M * dy_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;
+    p.M = (int)M;
+    p.n_tile = 128; p.kwin = 128;
+    p.part = workspace; p.splitK = splitK;
+    p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
+    p.kb_per_split = (p.KBp + splitK - 1) / splitK;
+    p.x_vec = bts_aligned16(x) && (x_pixel_stride % 4 == 0);
+    p.dy_vec = bts_aligned16(dy) && (dy_pixel_stride % 4 == 0);
+    p.precision = precision;
+    const int taps = KH * KW;
+    p.stage_bytes = 2 * A_BYTES + 2 * 4 * CHUNK_BYTES;
+    p.stages = (SMEM_LIMIT - 1024 - 2 * BLOCK_CI * 4 - 256) / p.stage_bytes;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    const int smem = p.stages * p.stage_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
+    dim3 grid(1, width / 128, taps * splitK);
+    if (grid.z > 65535) return BTS_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t err = cudaSuccess;
+    const bool vec = p.x_vec && p.dy_vec;
+#define BTS_LAUNCH_G(VEC)                                                                                            \
+    do {                                                                                                             \
+        static bool attr_set_[BTS_MAX_DEVICES] = {};                                                                 \
+        bool &attr_set = attr_set_[bts_cur_device()];                                                                \
+        if (!attr_set) {                                                                                             \
+            err = cudaFuncSetAttribute(wgrad_tc_kernel<0, false, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                       SMEM_LIMIT);                                                                  \
+            if (err != cudaSuccess) return (int)err;                                                                 \
+            attr_set = true;                                                                                         \
+        }                                                                                                            \
+        wgrad_tc_kernel<0, false, VEC><<<grid, NUM_THREADS, smem, st>>>(p);                                          \
+    } while (0)
+    if (vec) BTS_LAUNCH_G(true); else BTS_LAUNCH_G(false);
+#undef BTS_LAUNCH_G
+    BTS_LAUNCH_CHECK();
+    const long long total = (long long)taps * width * cpg;
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (g > cap) g = cap;
+    wgrad_reduce_grouped_kernel<<<(int)g, 256, 0, st>>>(workspace, splitK, taps, width, 128, cpg, KW, dw, s_co, s_ci, s_kh, s_kw);
     BTS_LAUNCH_CHECK();
     return 0;
 }

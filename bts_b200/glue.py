@@ -285,3 +285,69 @@ class _AvgPool2(torch.autograd.Function):
 
 def avgpool2(x):
     return _AvgPool2.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------ ResNet / ResNeXt glue
+class _MaxPool3s2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x, xs = _nhwc(x)
+        B, C, H, W = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = _new(B, C, Ho, Wo, x.device)
+        arg = torch.empty(B * Ho * Wo * C, device=x.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().bts_maxpool3s2_fwd(_ptr(x), xs, B, H, W, C, _ptr(y), C, _ptr(arg), _stream()), "bts_maxpool3s2_fwd")
+        _lib.count()
+        ctx.shape = (B, C, H, W)
+        ctx.save_for_backward(arg)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        g, gs = _nhwc(g)
+        gx = _new(B, C, H, W, g.device)
+        _lib.check(_lib.lib().bts_maxpool3s2_bwd(_ptr(g), gs, _ptr(arg), B, H, W, C, _ptr(gx), C, _stream()), "bts_maxpool3s2_bwd")
+        _lib.count()
+        return gx
+
+
+def maxpool3s2(x):
+    """3x3 / stride 2 / pad 1 max-pool (torchvision densenet `pool0`, resnet `maxpool`) on our NHWC kernels"""
+    return _MaxPool3s2.apply(x)
+
+
+class _BnAddRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, bn):
+        x, xs = _nhwc(x)
+        res, rs = _nhwc(res)
+        B, C, H, W = x.shape
+        n = B * H * W
+        batch = bn_uses_batch_stats(bn)
+        st = bn_finalize(bn_stats(x) if batch else None, n, bn, gamma, beta, batch)
+        y = _new(B, C, H, W, x.device)
+        _lib.check(_lib.lib().bts_bn_add_relu(_ptr(x), xs, n, C, _ptr(st[0]), _ptr(st[1]), _ptr(res), rs, _ptr(y), C, _stream()),
+                   "bts_bn_add_relu")
+        _lib.count()
+        ctx.batch = batch
+        ctx.save_for_backward(x, st, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, st, y = ctx.saved_tensors
+        g, gs = _nhwc(gy)
+        B, C, H, W = y.shape
+        gm = _new(B, C, H, W, y.device)
+        _lib.check(_lib.lib().bts_relu_bwd(_ptr(g), gs, _ptr(y), C, B * H * W, C, _ptr(gm), C, _stream()), "bts_relu_bwd")
+        _lib.count()
+        gx, S = bn_backward(x, gm, st, ctx.batch, False)
+        return (gx if ctx.needs_input_grad[0] else None, gm if ctx.needs_input_grad[1] else None,
+                S[1].float() if ctx.needs_input_grad[2] else None, S[0].float() if ctx.needs_input_grad[3] else None, None)
+
+
+def bn_add_relu(x, res, bn):
+    """relu(bn(x) + res): the tail of a torchvision Bottleneck, one streaming kernel after the statistics"""
+    return _BnAddRelu.apply(x, res, bn.weight, bn.bias, bn)

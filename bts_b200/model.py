@@ -58,14 +58,19 @@ class Conv2dTC(nn.Conv2d):
     weights_init_xavier (bts_main.py:338), state_dict keys and optimizer groups behave exactly as in the reference."""
 
     def forward(self, x):
-        if (x.is_cuda and x.dtype == torch.float32 and self.groups == 1
+        if (x.is_cuda and x.dtype == torch.float32
                 and self.bias is None and self.stride[0] == self.stride[1] and self.padding[0] == self.padding[1]
                 and self.dilation[0] == self.dilation[1] and self.kernel_size[0] == self.kernel_size[1]
-                and isinstance(self.padding, tuple) and self.padding_mode == "zeros"):
+                and isinstance(self.padding, tuple) and self.padding_mode == "zeros" and self.stride[0] in (1, 2)):
             from . import conv
-            if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
-                return conv.conv_c1(x, self.weight, sigmoid=False)
-            return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0])
+            if self.groups == 1:
+                if conv.c1_eligible(self.weight, self.stride[0], self.padding[0], self.dilation[0]):
+                    return conv.conv_c1(x, self.weight, sigmoid=False)
+                return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0])
+            cpg = self.in_channels // self.groups
+            if (self.in_channels == self.out_channels and cpg >= 4 and conv.group_window(self.out_channels, cpg) == 128):
+                # ResNeXt grouped 3x3 (32 groups): block-diagonal operator on the engine, fwd / dgrad / wgrad
+                return conv.conv2d(x, self.weight, self.stride[0], self.padding[0], self.dilation[0], groups=self.groups)
         # shapes the engine does not cover (bias / asymmetric geometry): the library conv, pinned to true fp32 for parity
         with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, allow_tf32=False):
             return super().forward(x)
@@ -100,6 +105,41 @@ class BatchNormTC(nn.BatchNorm2d):
 
 class ReluFolded(nn.Identity):
     """stands where torchvision's `relu0` was: the ReLU already ran inside the preceding BatchNormTC"""
+
+
+class MaxPoolTC(nn.MaxPool2d):
+    """the encoder stems' 3x3 / stride 2 / pad 1 max-pool (densenet `pool0`, resnet `maxpool`) on our NHWC kernels"""
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else self.kernel_size[0]
+        st = self.stride if isinstance(self.stride, int) else self.stride[0]
+        pd = self.padding if isinstance(self.padding, int) else self.padding[0]
+        if fuse_enabled(x) and (k, st, pd) == (3, 2, 1) and self.dilation in (1, (1, 1)) and not self.ceil_mode \
+                and not self.return_indices:
+            from . import glue
+            return glue.maxpool3s2(x)
+        return super().forward(x)
+
+
+def _bottleneck_class():
+    from torchvision.models.resnet import Bottleneck
+
+    class BottleneckTC(Bottleneck):
+        """torchvision ResNet / ResNeXt bottleneck [1x1 -> BN -> ReLU -> (grouped) 3x3 -> BN -> ReLU -> 1x1 -> BN -> +id ->
+        ReLU]: every conv on the tcgen05 engine (the grouped 3x3 as a block-diagonal operator), BN(+ReLU) and the
+        BN + residual + ReLU tail on our streaming kernels; parameters / buffers / state_dict untouched."""
+
+        def forward(self, x):
+            if not fuse_enabled(x):
+                return super().forward(x)
+            from . import glue
+            out = glue.bn_act(self.conv1(x), self.bn1, relu=True)
+            out = glue.bn_act(self.conv2(out), self.bn2, relu=True)
+            out = self.conv3(out)
+            identity = x if self.downsample is None else self.downsample(x)
+            return glue.bn_add_relu(out, identity, self.bn3)
+
+    return Bottleneck, BottleneckTC
 
 
 def _transition_class():
@@ -139,6 +179,8 @@ def adopt_convs(module):
     module tree in place -- parameter names, shapes and init are untouched."""
     base, fusedcls = _dense_block_class()
     tbase, tcls = _transition_class()
+    bbase, bcls = _bottleneck_class()
+    resnet = any(type(m) is bbase for m in module.modules())
     for m in module.modules():
         if type(m) is nn.Conv2d:
             m.__class__ = Conv2dTC
@@ -146,6 +188,16 @@ def adopt_convs(module):
             m.__class__ = fusedcls
         elif type(m) is tbase:
             m.__class__ = tcls
+        elif type(m) is bbase:
+            m.__class__ = bcls
+        elif type(m) is nn.MaxPool2d:
+            m.__class__ = MaxPoolTC
+        elif resnet and type(m) is nn.BatchNorm2d:
+            m.__class__ = BatchNormTC          # stem bn1, bottleneck BNs (when not fused), downsample BNs
+    # ResNet stem: bn1 (+ relu folded: the module named `relu` -- the H/2 skip tap -- then passes the activated tensor on)
+    if resnet and hasattr(module, "bn1") and isinstance(getattr(module, "relu", None), nn.ReLU):
+        module.bn1._fuse_relu = True
+        module.relu = ReluFolded()
     # DenseNet `features`: norm0 (+ relu0 folded) and norm5 on the streaming BatchNorm kernels
     if isinstance(module, nn.Sequential) and hasattr(module, "norm0") and type(module.norm0) is nn.BatchNorm2d:
         module.norm0.__class__ = BatchNormTC

@@ -118,10 +118,35 @@ int bts_conv_fwd_stats(const float *x, long long x_pixel_stride, int B, int Hs, 
                        long long out_pixel_stride, int act, int precision, double *stat_sum, double *stat_sumsq,
                        void *stream);
 
+/* General form of bts_conv_fwd (replaces cuDNN's strided-dgrad and grouped-convolution paths behind the ResNet / ResNeXt
+ * encoders, reference pytorch/bts.py:282-296 via torchvision.models.resnet):
+ *   source_mode 0 plain | 1 nearest x2 up-sample folded in | 2 ZERO-STUFFED x2 source with an explicit out_h x out_w output:
+ *       with the transposed, tap-flipped packed operator, stride = 1 and pad' = dil*(K-1) - pad this is the input gradient
+ *       of a STRIDE-2 convolution whose input was out_h x out_w (x = dY of that layer);
+ *   kwin > 0 block-diagonal ("grouped") operator packed by bts_conv_pack_weights_grouped: output channels
+ *       [nt*kwin, (nt+1)*kwin) read input channels [nt*kwin, (nt+1)*kwin) only; Cin == Cout == the layer width;
+ *   stat_sum / stat_sumsq as in bts_conv_fwd_stats (or both NULL). */
+int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int source_mode, int out_h, int out_w,
+                    int kwin, int Cin, int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                    const float *pre_scale, const float *pre_shift, int pre_relu, float *out, long long out_pixel_stride,
+                    int act, int precision, double *stat_sum, double *stat_sumsq, void *stream);
+/* grouped 3x3 (ResNeXt: 32 groups of cpg channels): w is (width, cpg, KH, KW).  bts_conv_group_window -> the diagonal block
+ * width kwin the packed operator uses (128 when width % 128 == 0 and 128 % cpg == 0; 0 = not supported). */
+int bts_conv_group_window(int width, int cpg);
+long long bts_conv_packed_floats_grouped(int width, int cpg, int KH, int KW);
+int bts_conv_pack_weights_grouped(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw, int width,
+                                  int cpg, int KH, int KW, int transpose_flip, float *wpack, void *stream);
+int bts_conv_wgrad_grouped_plan(int B, int Hout, int Wout, int width, int cpg, int KH, int KW, int *splitK_out,
+                                long long *workspace_floats);
+int bts_conv_wgrad_grouped(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int width, int cpg, int KH, int KW,
+                           int stride, int pad, int dil, const float *dy, long long dy_pixel_stride, float *workspace,
+                           int splitK, float *dw, long long s_co, long long s_ci, long long s_kh, long long s_kw,
+                           int precision, void *stream);
+
 /* wgrad on the same engine: dW[co,ci,tap] = sum_p dY[p,co] * pre(x[p (+) tap, ci]), MN-major tcgen05 operands,
  * split-K partials in `workspace` reduced deterministically into dw (strides in floats).
  *   bts_conv_wgrad_plan(...) -> splitK and the workspace size (floats) the call needs. */
-int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int *splitK_out,
+int bts_conv_wgrad_plan(int B, int Hout, int Wout, int Cin, int Cout, int KH, int KW, int stride, int *splitK_out,
                         long long *workspace_floats);
 int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int Cin,
                    int KH, int KW, int stride, int pad, int dil, const float *pre_scale, const float *pre_shift,
@@ -209,6 +234,20 @@ int bts_conv_pw_wgrad_eligible(int Cin, int Cout);
 long long bts_conv_pw_wgrad_workspace_floats(int Cin, int Cout);
 int bts_conv_pw_wgrad(const float *x, long long x_pixel_stride, const float *dy, long long dy_pixel_stride, long long M,
                       int Cin, int Cout, float *workspace, float *dw, long long s_co, long long s_ci, void *stream);
+
+/* ResNet / ResNeXt encoder glue (torchvision.models.resnet behind reference pytorch/bts.py:282-296):
+ *   bts_bn_add_relu   out = max(x*scale + shift + res, 0)            Bottleneck tail  relu(bn3(conv3(.)) + identity)
+ *   bts_relu_bwd      out = gy * (y > 0)                             its backward (through the saved output y)
+ *   bts_maxpool3s2_*  3x3 / stride 2 / pad 1 max-pool (the encoder stems' pool0 / maxpool), NHWC; forward records the
+ *                     winning window position (uint8 per OUTPUT element, dense [B,Ho,Wo,C]) -> deterministic gather backward */
+int bts_bn_add_relu(const float *x, long long x_pixel_stride, long long M, int C, const float *scale, const float *shift,
+                    const float *res, long long res_pixel_stride, float *out, long long out_pixel_stride, void *stream);
+int bts_relu_bwd(const float *gy, long long gy_pixel_stride, const float *y, long long y_pixel_stride, long long M, int C,
+                 float *out, long long out_pixel_stride, void *stream);
+int bts_maxpool3s2_fwd(const float *x, long long x_pixel_stride, int B, int H, int W, int C, float *out,
+                       long long out_pixel_stride, unsigned char *argmax, void *stream);
+int bts_maxpool3s2_bwd(const float *g, long long g_pixel_stride, const unsigned char *argmax, int B, int H, int W, int C,
+                       float *gx, long long gx_pixel_stride, void *stream);
 
 #ifdef __cplusplus
 }
