@@ -533,12 +533,30 @@ def _run_ours(args):
     else:
         model.eval()
     model.to(dev)
-    if world > 1 and train:
-        # bts_main.py:352 passes find_unused_parameters=True because the ResNet/ResNeXt encoders keep a never-used `fc`
-        # (SURVEY Q11); DenseNet-161 has no unused parameter, so the extra autograd traversal is switched off here.
+    red = bcast = None
+    if world > 1 and train and args.reducer == "ddp":
+        # exactly the reference's wrap.  bts_main.py:352 passes find_unused_parameters=True because the ResNet/ResNeXt
+        # encoders keep a never-used `fc`; DenseNet-161 has no unused parameter, so the extra autograd
+        # traversal is switched off here.
         unused = any(k.startswith("encoder.base_model.fc") for k, _ in model.named_parameters())
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=unused,
                                                           gradient_as_bucket_view=True)
+    elif world > 1 and train:
+        # B200-native schedule (bts_b200/dist.py): ONE all-reduce of the flat gradient vector after backward and one flat
+        # broadcast of rank 0's BatchNorm buffers before forward -- the same two collectives DDP issues (C1, C3 of SURVEY
+        # 2.5), un-bucketed: the persistent 1-CTA-per-SM conv kernels leave NCCL no SM to overlap on anyway.
+        from bts_b200 import dist as D
+        with torch.no_grad():
+            ps = list(model.parameters())
+            flat = torch.cat([q.detach().reshape(-1) for q in ps])
+            dist.broadcast(flat, 0)                                      # C2: initial parameter broadcast
+            o = 0
+            for q in ps:
+                q.copy_(flat[o:o + q.numel()].view_as(q))
+                o += q.numel()
+            del flat
+        red = D.FlatGradReducer(model.parameters())
+        bcast = D.FlatBufferBroadcaster(model)
     opt = make_optimizer(model, torch) if train else None
     crit = bts.silog_loss(0.85)
     B = cfg["B"]
@@ -551,9 +569,13 @@ def _run_ours(args):
             with torch.no_grad():
                 return model(x, f)[4].sum()
         opt.zero_grad()
+        if bcast is not None:
+            bcast.broadcast(0)
         out = model(x, f)
         loss = crit(out[4], g, g > cfg["thr"])
         loss.backward()
+        if red is not None:
+            red.reduce()
         lr = (1e-4 - 1e-5) * (1 - i / total_steps) ** 0.9 + 1e-5
         for grp in opt.param_groups:
             grp["lr"] = lr
@@ -604,6 +626,9 @@ def _run_ours(args):
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "collective": ("none" if world == 1 or not train else
+                                  ("torch DDP (25 MB buckets, overlapped)" if args.reducer == "ddp" else
+                                   "one NCCL all-reduce (AVG) of the flat gradient vector per step + one flat buffer broadcast")),
                    "l2": "no explicit flush: per-step working set (saved activations, GBs) >> 126 MB L2",
                    "precision": "3xTF32 split on tcgen05 (fp32-grade, parity mode)"},
         "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
@@ -681,6 +706,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="K16", choices=sorted(CONFIGS) + ["LPG"])
+    ap.add_argument("--reducer", default="flat", choices=["flat", "ddp"],
+                    help="N>1: flat = one all-reduce of the flat gradient vector (bts_b200/dist.py); ddp = torch DDP as bts_main.py")
     ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager/cuDNN reference leg")
