@@ -90,11 +90,15 @@ def synth_batch(cfg, B, seed, dev="cpu", pin=False):
     return img.to(dev), focal.to(dev), gt.to(dev)
 
 
-def make_optimizer(model, torch):
-    """bts_main.py:371-373 (lr 1e-4, eps 1e-3, wd 1e-2 encoder / 0 decoder: arguments_train_eigen.txt)."""
+def make_optimizer(model, torch, fused=False):
+    """bts_main.py:371-373 (lr 1e-4, eps 1e-3, wd 1e-2 encoder / 0 decoder: arguments_train_eigen.txt).
+    fused: bts_b200.optim.FusedAdamW -- the same optimizer (state_dict-compatible, ulp-level parity test) as one kernel."""
     m = model.module if hasattr(model, "module") else model
-    return torch.optim.AdamW([{"params": m.encoder.parameters(), "weight_decay": 1e-2},
-                              {"params": m.decoder.parameters(), "weight_decay": 0}], lr=1e-4, eps=1e-3)
+    groups = [{"params": m.encoder.parameters(), "weight_decay": 1e-2}, {"params": m.decoder.parameters(), "weight_decay": 0}]
+    if fused:
+        from bts_b200.optim import FusedAdamW
+        return FusedAdamW(groups, lr=1e-4, eps=1e-3)
+    return torch.optim.AdamW(groups, lr=1e-4, eps=1e-3)
 
 
 def freeze_like_set_misc(model):
@@ -557,7 +561,7 @@ def _run_ours(args):
             del flat
         red = D.FlatGradReducer(model.parameters())
         bcast = D.FlatBufferBroadcaster(model)
-    opt = make_optimizer(model, torch) if train else None
+    opt = make_optimizer(model, torch, fused=(args.optimizer == "fused")) if train else None
     crit = bts.silog_loss(0.85)
     B = cfg["B"]
     img, focal, gt = synth_batch(cfg, B, 1 + rank, dev)
@@ -630,7 +634,9 @@ def _run_ours(args):
                                   ("torch DDP (25 MB buckets, overlapped)" if args.reducer == "ddp" else
                                    "one NCCL all-reduce (AVG) of the flat gradient vector per step + one flat buffer broadcast")),
                    "l2": "no explicit flush: per-step working set (saved activations, GBs) >> 126 MB L2",
-                   "precision": "3xTF32 split on tcgen05 (fp32-grade, parity mode)"},
+                   "precision": "3xTF32 split on tcgen05 (fp32-grade, parity mode)",
+                   "optimizer": ("bts_b200.optim.FusedAdamW (one multi-tensor kernel + one re-pack launch)"
+                                 if args.optimizer == "fused" else "torch.optim.AdamW") if train else "none"},
         "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e / K, "ms_per_step_median": statistics.median(per_e)},
         "repeats": {"ms_per_step_median": statistics.median(per), "ms_per_step_min": per[0], "ms_per_step_max": per[-1],
@@ -708,6 +714,8 @@ def main():
     ap.add_argument("--config", default="K16", choices=sorted(CONFIGS) + ["LPG"])
     ap.add_argument("--reducer", default="flat", choices=["flat", "ddp"],
                     help="N>1: flat = one all-reduce of the flat gradient vector (bts_b200/dist.py); ddp = torch DDP as bts_main.py")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused = bts_b200.optim.FusedAdamW (default), torch = torch.optim.AdamW exactly as bts_main.py")
     ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager/cuDNN reference leg")

@@ -110,6 +110,9 @@ SIGNATURES = {
     "bts_relu_bwd": [_p, _ll, _p, _ll, _ll, _i, _p, _ll, _p],
     "bts_maxpool3s2_fwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p, _p],
     "bts_maxpool3s2_bwd": [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p],
+    "bts_adamw_chunk": [],
+    "bts_adamw_multi": [_p, _p, _p, _i, _p, _p, _i, _p, _i, _p],
+    "bts_conv_pack_weights_multi": [_p, _i, _ll, _p],
     "bts_conv_pw_wgrad_eligible": [_i, _i],
     "bts_conv_pw_wgrad_workspace_floats": [_i, _i],
     "bts_conv_pw_wgrad": [_p, _ll, _p, _ll, _ll, _i, _i, _p, _p, _ll, _ll, _p],

@@ -94,10 +94,9 @@ using namespace tc;
 // ceil32(Kch): conv1 (Cin 36) 11 k-blocks instead of 18, the 3x3 dgrad of the dense layers (48) 14 instead of 18,
 // the 7x7 stem (Cin 3) 7 instead of 49.  Identical to the per-tap 32-channel chunking whenever Kch % 32 == 0.
 // transpose_flip=1 packs the dgrad operator: rows = ci, k = (flipped tap, co).
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
-                                                           long long s_kh, long long s_kw, int Cout, int Cin, int KH,
-                                                           int KW, int transpose_flip, float *__restrict__ wpack,
-                                                           int n_tile, int n_tiles, int kwin, int cpg) {
+__device__ __forceinline__ void pack_one(const float *__restrict__ w, long long s_co, long long s_ci, long long s_kh,
+                                         long long s_kw, int Cout, int Cin, int KH, int KW, int transpose_flip,
+                                         float *__restrict__ wpack, int n_tile, int kwin, int cpg, long long idx) {
     // grouped (kwin > 0): Cin == Cout == total width, w is (width, cpg, KH, KW); rows = all channels, the K channels of
     // n-tile nt are the window [nt*kwin, (nt+1)*kwin) and entries outside the row's group are zero (block diagonal)
     const int Nrows = transpose_flip ? Cin : Cout;    // GEMM N
@@ -105,44 +104,76 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
     const int CQ = (Kch + 3) / 4;
     const int taps = KH * KW;
     const int KB = (taps * CQ + 7) / 8;
+    const int kk = (int)(idx & 31);
+    long long t = idx >> 5;
+    const int n = (int)(t % n_tile);
+    t /= n_tile;
+    const int kb = (int)(t % KB);
+    const int nt = (int)(t / KB);
+    const int g = kb * 8 + (kk >> 2);
+    const int tap = g / CQ;
+    const int row = nt * n_tile + n, ch = (g - tap * CQ) * 4 + (kk & 3);
+    float val = 0.f;
+    if (row < Nrows && tap < taps && ch < Kch) {
+        int kh = tap / KW, kw = tap % KW;
+        long long off;
+        bool live = true;
+        int kc = ch, rr = row;            // K channel / row index into w's (co, ci) axes
+        if (kwin) {
+            const int kglob = nt * kwin + ch;                 // global channel on the K side
+            live = (kglob / cpg) == (row / cpg);
+            if (transpose_flip) { kc = kglob; rr = row % cpg; }   // w[co = kglob][ci_local = row % cpg]
+            else { kc = kglob % cpg; }                            // w[co = row][ci_local = kglob % cpg]
+        }
+        if (transpose_flip) {
+            kh = KH - 1 - kh; kw = KW - 1 - kw;
+            off = (long long)kc * s_co + (long long)rr * s_ci + kh * s_kh + kw * s_kw;
+        } else {
+            off = (long long)rr * s_co + (long long)kc * s_ci + kh * s_kh + kw * s_kw;
+        }
+        if (live) val = w[off];
+    }
+    const float hi = rna_tf32(val);
+    const float lo = rna_tf32(val - hi);
+    const size_t tile = ((size_t)nt * KB + kb) * 2 * (size_t)n_tile * 32;
+    const size_t in_tile = (size_t)n * 32 + (size_t)(((kk >> 2) ^ (n & 7)) << 2) + (kk & 3);
+    wpack[tile + in_tile] = hi;
+    wpack[tile + (size_t)n_tile * 32 + in_tile] = lo;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
+                                                           long long s_kh, long long s_kw, int Cout, int Cin, int KH,
+                                                           int KW, int transpose_flip, float *__restrict__ wpack,
+                                                           int n_tile, int n_tiles, int kwin, int cpg) {
+    const int Kch = kwin ? kwin : (transpose_flip ? Cout : Cin);
+    const int KB = (KH * KW * ((Kch + 3) / 4) + 7) / 8;
     const long long total = (long long)n_tiles * KB * n_tile * 32;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x)
+        pack_one(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW, transpose_flip, wpack, n_tile, kwin, cpg, idx);
+}
+
+// every packed operator of a model in ONE launch (after an optimizer step: 394 launches -> 1 for DenseNet-161 + decoder)
+struct PackDesc {
+    const float *w;
+    float *wpack;
+    long long s_co, s_ci, s_kh, s_kw;
+    long long start;                     // first global index of this operator (prefix sum of packed_floats / 2)
+    int Cout, Cin, KH, KW, transpose_flip, n_tile, n_tiles, kwin, cpg, pad_;
+};
+static_assert(sizeof(PackDesc) == 96, "PackDesc layout is mirrored by bts_b200/conv.py");
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc *__restrict__ d, int n, long long total) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int kk = (int)(idx & 31);
-        long long t = idx >> 5;
-        const int n = (int)(t % n_tile);
-        t /= n_tile;
-        const int kb = (int)(t % KB);
-        const int nt = (int)(t / KB);
-        const int g = kb * 8 + (kk >> 2);
-        const int tap = g / CQ;
-        const int row = nt * n_tile + n, ch = (g - tap * CQ) * 4 + (kk & 3);
-        float val = 0.f;
-        if (row < Nrows && tap < taps && ch < Kch) {
-            int kh = tap / KW, kw = tap % KW;
-            long long off;
-            bool live = true;
-            int kc = ch, rr = row;            // K channel / row index into w's (co, ci) axes
-            if (kwin) {
-                const int kglob = nt * kwin + ch;                 // global channel on the K side
-                live = (kglob / cpg) == (row / cpg);
-                if (transpose_flip) { kc = kglob; rr = row % cpg; }   // w[co = kglob][ci_local = row % cpg]
-                else { kc = kglob % cpg; }                            // w[co = row][ci_local = kglob % cpg]
-            }
-            if (transpose_flip) {
-                kh = KH - 1 - kh; kw = KW - 1 - kw;
-                off = (long long)kc * s_co + (long long)rr * s_ci + kh * s_kh + kw * s_kw;
-            } else {
-                off = (long long)rr * s_co + (long long)kc * s_ci + kh * s_kh + kw * s_kw;
-            }
-            if (live) val = w[off];
+        int lo = 0, hi = n - 1;                                    // last descriptor with start <= idx
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (d[mid].start <= idx) lo = mid; else hi = mid - 1;
         }
-        const float hi = rna_tf32(val);
-        const float lo = rna_tf32(val - hi);
-        const size_t tile = ((size_t)nt * KB + kb) * 2 * (size_t)n_tile * 32;
-        const size_t in_tile = (size_t)n * 32 + (size_t)(((kk >> 2) ^ (n & 7)) << 2) + (kk & 3);
-        wpack[tile + in_tile] = hi;
-        wpack[tile + (size_t)n_tile * 32 + in_tile] = lo;
+        const PackDesc &q = d[lo];
+        pack_one(q.w, q.s_co, q.s_ci, q.s_kh, q.s_kw, q.Cout, q.Cin, q.KH, q.KW, q.transpose_flip, q.wpack, q.n_tile, q.kwin,
+                 q.cpg, idx - q.start);
     }
 }
 
@@ -752,4 +783,15 @@ extern "C" int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, 
     return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, source_mode, out_h, out_w, kwin, Cin, KH, KW, stride, pad, dil, wpack,
                          Cout, pre_scale, pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq,
                          stream);
+}
+
+// descs: device array of n PackDesc (layout above; built by the host side once per model), total = sum of packed_floats / 2
+extern "C" int bts_conv_pack_weights_multi(const void *descs, int n, long long total, void *stream) {
+    if (!descs || n < 1 || total < 1) return BTS_EINVAL;
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    pack_weights_multi_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackDesc *>(descs), n, total);
+    BTS_LAUNCH_CHECK();
+    return 0;
 }

@@ -249,6 +249,20 @@ int bts_maxpool3s2_fwd(const float *x, long long x_pixel_stride, int B, int H, i
 int bts_maxpool3s2_bwd(const float *g, long long g_pixel_stride, const unsigned char *argmax, int B, int H, int W, int C,
                        float *gx, long long gx_pixel_stride, void *stream);
 
+/* ---- optimizer step of the training loop (reference pytorch/bts_main.py:371-373 torch.optim.AdamW, two groups, eps 1e-3;
+ * :456-460 poly LR) as ONE multi-tensor kernel, csrc/optim.cu.  ptrs: device int64 [4n] = param | grad | exp_avg | exp_avg_sq
+ * addresses; numel: device int64 [n]; group: device int32 [n] -> index into the n_groups (<= 8) scalar sets;
+ * chunk_tensor / chunk_off: device tables cutting every tensor into bts_adamw_chunk()-element pieces;
+ * scalars: HOST float [7*n_groups], seven blocks of n_groups: 1-lr*wd | 1-beta1 | beta2 | 1-beta2 | sqrt(1-beta2^t) | eps |
+ * -lr/(1-beta1^t).  Element arithmetic follows torch's _multi_tensor_adam operation by operation. */
+int bts_adamw_chunk(void);
+int bts_adamw_multi(const long long *ptrs, const long long *numel, const int *group, int n, const int *chunk_tensor,
+                    const long long *chunk_off, int n_chunks, const float *scalars, int n_groups, void *stream);
+/* every packed conv operator of a model in one launch: descs = device array of n 96-byte descriptors
+ * {w, wpack, s_co, s_ci, s_kh, s_kw, start (int64 each), Cout, Cin, KH, KW, transpose_flip, n_tile, n_tiles, kwin, cpg, pad
+ * (int32 each)}, start = prefix sum of packed_floats/2; total = their sum. */
+int bts_conv_pack_weights_multi(const void *descs, int n, long long total, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
