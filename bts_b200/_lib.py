@@ -110,6 +110,10 @@ SIGNATURES = {
     "bts_relu_bwd": [_p, _ll, _p, _ll, _ll, _i, _p, _ll, _p],
     "bts_maxpool3s2_fwd": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p, _p],
     "bts_maxpool3s2_bwd": [_p, _ll, _p, _i, _i, _i, _i, _p, _ll, _p],
+    "bts_fill_zero_f32": [_p, _ll, _p],
+    "bts_input_prep": [_p, _i, _i, _p, _f, _p, _i, _i, _i, _p, _ll, _p, _p],
+    "bts_eval_errors": [_p, _p, _i, _i, _f, _f, _i, _i, _i, _i, _p, _p, _p],
+    "bts_depth_to_u16": [_p, _f, _ll, _p, _p],
     "bts_adamw_chunk": [],
     "bts_adamw_multi": [_p, _p, _p, _i, _p, _p, _i, _p, _i, _p],
     "bts_conv_pack_weights_multi": [_p, _i, _ll, _p],

@@ -38,3 +38,11 @@ extern "C" int bts_version(char *buf, int buflen) {
     }
     return 100;
 }
+
+// zero n floats on the stream (grad_focal of the TF-op surface: `focal` never enters the LPG arithmetic)
+extern "C" int bts_fill_zero_f32(float *p, long long n, void *stream) {
+    if (n < 0 || (n > 0 && !p)) return BTS_EINVAL;
+    if (n == 0) return 0;
+    const cudaError_t e = cudaMemsetAsync(p, 0, sizeof(float) * (size_t)n, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : (int)e;
+}

@@ -160,3 +160,56 @@ class _Silog(torch.autograd.Function):
 
 def silog(depth_est, depth_gt, mask, variance_focus):
     return _Silog.apply(depth_est, depth_gt, mask, float(variance_focus))
+
+
+# ------------------------------------------------------------------------------------------------ data formats
+def input_prep(img_u8, params, out_hw, depth_u16=None, depth_div=1000.0):
+    """reference loader transform on the GPU (pytorch/bts_dataloader.py:128-140,202-235,244-249): img_u8 (B,Hs,Ws,3) uint8
+    CUDA, params (B,9) fp32 = y0,x0,flip,augment,gamma,brightness,colour rgb -> (image (B,3,H,W) channels_last fp32,
+    depth (B,1,H,W) fp32 in metres or None)"""
+    _need_cuda(img_u8, params)
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[3] != 3 or not img_u8.is_contiguous():
+        raise ValueError("img_u8 must be a contiguous (B,Hs,Ws,3) uint8 tensor")
+    B, Hs, Ws, _ = img_u8.shape
+    H, W = out_hw
+    params = params.contiguous().float()
+    if tuple(params.shape) != (B, 9):
+        raise ValueError("params must be (B,9)")
+    img = torch.empty((B, 3, H, W), device=img_u8.device, dtype=torch.float32).contiguous(memory_format=torch.channels_last)
+    dep = None
+    if depth_u16 is not None:
+        if depth_u16.dtype not in (torch.uint16, torch.int16) or tuple(depth_u16.shape) != (B, Hs, Ws):
+            raise ValueError("depth_u16 must be (B,Hs,Ws) uint16")
+        depth_u16 = depth_u16.contiguous()
+        dep = torch.empty((B, 1, H, W), device=img_u8.device, dtype=torch.float32)
+    _lib.check(_lib.lib().bts_input_prep(_ptr(img_u8), Hs, Ws, _ptr(depth_u16), float(depth_div), _ptr(params), B, H, W,
+                                         _ptr(img), 3, _ptr(dep), _stream()), "bts_input_prep")
+    _lib.count()
+    return img, dep
+
+
+def eval_errors(pred, gt, min_depth, max_depth, crop=None):
+    """the nine eval metrics of one image + valid-pixel count, on the GPU (pytorch/bts_main.py:144-165,275-296).
+    pred, gt: (H,W) fp32 CUDA; crop = (y0,y1,x0,x1) or None.  Returns a 10-float CUDA tensor (no host sync)."""
+    _need_cuda(pred, gt)
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    H, W = pred.shape[-2], pred.shape[-1]
+    if pred.numel() != H * W or gt.numel() != H * W:
+        raise ValueError("eval_errors takes one image at a time")
+    y0, y1, x0, x1 = crop if crop is not None else (0, H, 0, W)
+    ws = torch.empty(10, device=pred.device, dtype=torch.float64)
+    out = torch.empty(10, device=pred.device, dtype=torch.float32)
+    _lib.check(_lib.lib().bts_eval_errors(_ptr(pred), _ptr(gt), H, W, float(min_depth), float(max_depth), int(y0), int(y1),
+                                          int(x0), int(x1), _ptr(ws), _ptr(out), _stream()), "bts_eval_errors")
+    _lib.count(2)
+    return out
+
+
+def depth_to_u16(depth, scale):
+    """uint16(depth * scale): the 16-bit PNG wire format of bts_test.py:179-185 (scale 256 KITTI / 1000 NYU)"""
+    _need_cuda(depth)
+    depth = depth.contiguous().float()
+    out = torch.empty(depth.shape, device=depth.device, dtype=torch.uint16)
+    _lib.check(_lib.lib().bts_depth_to_u16(_ptr(depth), float(scale), depth.numel(), _ptr(out), _stream()), "bts_depth_to_u16")
+    _lib.count()
+    return out

@@ -263,6 +263,25 @@ int bts_adamw_multi(const long long *ptrs, const long long *numel, const int *gr
  * (int32 each)}, start = prefix sum of packed_floats/2; total = their sum. */
 int bts_conv_pack_weights_multi(const void *descs, int n, long long total, void *stream);
 
+/* ---- data formats either side of the hot path, csrc/io.cu
+ * bts_input_prep: the reference loader's per-sample transform after decoding (pytorch/bts_dataloader.py:128-140,202-235,
+ *   244-249), fused: uint8 HWC frames [B,Hs,Ws,3] (+ optional uint16 depth [B,Hs,Ws]) -> crop -> flip -> gamma/brightness/
+ *   colour augmentation + clip -> ImageNet normalisation -> fp32 NHWC image [B,H,W,(stride)] and depth/depth_div [B,H,W].
+ *   params: device float [B][9] = y0, x0, flip, augment, gamma, brightness, colour r,g,b (the random draws stay on the host).
+ * bts_eval_errors: online-eval clamps + masks + the nine metrics of one image (pytorch/bts_main.py:144-165,275-296):
+ *   metrics_out[10] = silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3, n_valid; crop rows [y0,y1) cols [x0,x1);
+ *   workspace = 10 doubles.
+ * bts_depth_to_u16: the 16-bit PNG wire format of pytorch/bts_test.py:179-185, uint16(depth * scale). */
+int bts_input_prep(const unsigned char *img_u8, int Hs, int Ws, const unsigned short *depth_u16, float depth_div,
+                   const float *params, int B, int H, int W, float *image_out, long long out_pixel_stride, float *depth_out,
+                   void *stream);
+int bts_eval_errors(const float *pred, const float *gt, int H, int W, float min_depth, float max_depth, int crop_y0,
+                    int crop_y1, int crop_x0, int crop_x1, double *workspace, float *metrics_out, void *stream);
+int bts_depth_to_u16(const float *depth, float scale, long long n, unsigned short *out, void *stream);
+
+/* zero n floats on the stream (grad_focal output of the TF-op surface, integration/tf_op/bts_lpg_tf_op.cc) */
+int bts_fill_zero_f32(float *p, long long n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
