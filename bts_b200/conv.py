@@ -163,11 +163,14 @@ def _nhwc_view(x):
 
 def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_shift=None, pre_relu=False,
               upsample2=False, act=None, out=None, precision=0, packed=None, cout=None, transpose_flip=False,
-              stats=None, groups=1, zero_stuff_out=None):
+              stats=None, groups=1, zero_stuff_out=None, bn_bwd=None):
     """Runs the engine.  x: (B,Cin,Hs,Ws) NHWC-in-memory fp32 CUDA.  Returns (B,Cout,Hout,Wout) channels_last.
     `out` may be a pre-allocated channels_last tensor or a channel slice of one (concat-free writes).
     `stats`: a ZEROED fp64 [2, Cout] tensor that receives per-channel (sum, sum of squares) of the output, reduced in the
     conv epilogue (Cout <= 256) -- the BatchNorm batch statistics of the tensor being produced.
+    `bn_bwd=(x_bn, st, relu)` (with a zeroed `stats`): the output is the gradient w.r.t. [relu](bn(x_bn)); the epilogue also
+    reduces the BatchNorm-backward sums S1 = sum g*mask, S2 = sum g*mask*xhat into stats[0], stats[1] (st = [4,C] from
+    bn_finalize) -- the separate reduce pass over (x, g) disappears.
     `groups` > 1: block-diagonal operator (ResNeXt 3x3).  `zero_stuff_out=(H,W)`: x is the gradient of a stride-2 layer
     whose input was HxW -- the source is read as its zero-stuffed x2 expansion (use with transpose_flip, stride 1)."""
     _need_cuda(x, weight)
@@ -213,6 +216,24 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
         pre_shift = pre_shift.contiguous()
     if stats is not None and (stats.dtype != torch.float64 or tuple(stats.shape) != (2, Co) or not stats.is_contiguous()):
         raise ValueError("stats must be a contiguous fp64 [2, Cout] tensor")
+    if bn_bwd is not None:
+        xb, st, relu = bn_bwd
+        xb, xbs = _nhwc_view(xb)
+        if stats is None or act is not None or pre_scale is not None or pre_relu or tuple(xb.shape) != (B, Co, Hout, Wout) \
+                or tuple(st.shape) != (4, Co) or not st.is_contiguous():
+            raise ValueError("bn_bwd needs zeroed stats, no act / pre-op, x_bn shaped like the output and st = [4, Cout]")
+        with torch.cuda.device(x.device):
+            rc = _traced("dgrad" if transpose_flip else "fwd",
+                         "%dx%dx%d %d->%d k%d d%d s%d%s bnb" % (B, Hs, Ws, Cin, Co, KH, dilation, stride, " zs" if mode == 2 else ""),
+                         lambda: _lib.lib().bts_conv_fwd_bnbwd(_ptr(x), xs, B, Hs, Ws, mode, Hout if mode == 2 else 0,
+                                                               Wout if mode == 2 else 0, kwin, Cin, KH, KW, stride, padding,
+                                                               dilation, _ptr(packed), Co, _ptr(out), os_, int(precision),
+                                                               _ptr(xb), xbs, _ptr(st), int(bool(relu)), _ptr(stats[0]),
+                                                               _ptr(stats[1]), _stream()),
+                         2.0 * B * Hout * Wout * Co * (Cin // groups) * KH * KW)
+        _lib.check(rc, "bts_conv_fwd_bnbwd")
+        _lib.count()
+        return out
     with torch.cuda.device(x.device):
         call = lambda: _lib.lib().bts_conv_fwd_ex(_ptr(x), xs, B, Hs, Ws, mode, Hout if mode == 2 else 0,
                                                   Wout if mode == 2 else 0, kwin, Cin, KH, KW, stride, padding, dilation,

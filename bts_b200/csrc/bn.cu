@@ -304,6 +304,16 @@ extern "C" int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const
     return 0;
 }
 
+// (k0, k1) coefficients of the backward apply pass from already-reduced sums (the reduction fused into a dgrad epilogue,
+// bts_conv_fwd_bnbwd)
+extern "C" int bts_bn_bwd_coef(const double *S1, const double *S2, long long M, int C, const float *scale, const float *mean,
+                               const float *invstd, float *coef, void *stream) {
+    if (!S1 || !S2 || !scale || !mean || !invstd || !coef || M < 1 || C < 1) return BTS_EINVAL;
+    bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S1, S2, M, C, scale, mean, invstd, coef);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
                                       long long M, int C, const float *scale, const float *shift, const float *mean,
                                       const float *invstd, double *S1, double *S2, float *coef, void *stream) {

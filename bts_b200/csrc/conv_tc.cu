@@ -79,6 +79,11 @@ struct ConvParams {
     int KB;                  // ceil(KH*KW*CQ / 8) k-blocks
     tc::FastDiv fd_cq, fd_kw;
     double *stat_sum, *stat_sumsq;   // optional per-output-channel sum / sum of squares of the (activated) output
+    // BatchNorm-backward reduction fused into a dgrad's epilogue (bnb_x != null): the tile being written is g = dL/d relu(bn(x));
+    // stat_sum[c] += sum_p g*[bn(x)>0],  stat_sumsq[c] += sum_p g*[bn(x)>0]*xhat   (bts_bn_relu_bwd_reduce without its pass)
+    const float *bnb_x; long long bnb_xs;
+    const float *bnb_st;             // [4][Cout]: scale, shift, mean, invstd
+    int bnb_relu;
     int stages, stage_bytes; // smem ring: as many (A hi/lo + B hi/lo) stages as fit
     tc::FastDiv fd_wout, fd_hout, fd_ntiles;
 };
@@ -533,14 +538,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 if (p.stat_sum) {
                     // BatchNorm batch statistics of the tensor being produced (bts_bn_stats fused into its producer):
                     // column sums over the warp's 32 rows by a transposing butterfly (16 shuffles per quantity instead
-                    // of 80), then shared-memory partials per CTA; flushed once per CTA with fp64 atomics below.
+                    // of 80), then shared-memory partials per CTA; flushed with fp64 atomics below.
                     // (host guarantees act == none here: the statistics are those of the raw conv output)
+                    // With bnb_x set the two quantities are instead the BatchNorm-BACKWARD sums of the gradient tile.
                     float s1[16], s2[16];
+                    if (p.bnb_x) {
+                        const int cb0 = nt * n_tile + cc;
+                        const float *xr = p.bnb_x + (m < p.M ? m : 0) * p.bnb_xs + cb0;
+                        const bool xvec = ((p.bnb_xs & 3) == 0) && ((((uintptr_t)p.bnb_x) & 15) == 0) && cb0 + 15 < p.Cout &&
+                                          ((p.Cout & 3) == 0);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const float a = m < p.M ? __uint_as_float(r[e]) : 0.f;
-                        s1[e] = a;
-                        s2[e] = a * a;
+                        for (int e4 = 0; e4 < 16; e4 += 4) {
+                            float xv[4], sc[4], sh[4], mu[4], is[4];
+                            if (xvec) {
+                                const float4 q4 = m < p.M ? __ldg(reinterpret_cast<const float4 *>(xr + e4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(p.bnb_st + cb0 + e4));
+                                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bnb_st + p.Cout + cb0 + e4));
+                                const float4 c4 = __ldg(reinterpret_cast<const float4 *>(p.bnb_st + 2 * p.Cout + cb0 + e4));
+                                const float4 d4 = __ldg(reinterpret_cast<const float4 *>(p.bnb_st + 3 * p.Cout + cb0 + e4));
+                                xv[0] = q4.x; xv[1] = q4.y; xv[2] = q4.z; xv[3] = q4.w;
+                                sc[0] = a4.x; sc[1] = a4.y; sc[2] = a4.z; sc[3] = a4.w;
+                                sh[0] = b4.x; sh[1] = b4.y; sh[2] = b4.z; sh[3] = b4.w;
+                                mu[0] = c4.x; mu[1] = c4.y; mu[2] = c4.z; mu[3] = c4.w;
+                                is[0] = d4.x; is[1] = d4.y; is[2] = d4.z; is[3] = d4.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int c = cb0 + e4 + e;
+                                    const bool ok = c < p.Cout;
+                                    const int ce = ok ? c : p.Cout - 1;
+                                    xv[e] = (ok && m < p.M) ? __ldg(xr + e4 + e) : 0.f;
+                                    sc[e] = __ldg(p.bnb_st + ce); sh[e] = __ldg(p.bnb_st + p.Cout + ce);
+                                    mu[e] = __ldg(p.bnb_st + 2 * p.Cout + ce); is[e] = __ldg(p.bnb_st + 3 * p.Cout + ce);
+                                }
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float gval = m < p.M ? __uint_as_float(r[e4 + e]) : 0.f;
+                                const float y = fmaf(xv[e], sc[e], sh[e]);
+                                const float gm = (!p.bnb_relu || y > 0.f) ? gval : 0.f;
+                                s1[e4 + e] = gm;
+                                s2[e4 + e] = gm * ((xv[e] - mu[e]) * is[e]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float a = m < p.M ? __uint_as_float(r[e]) : 0.f;
+                            s1[e] = a;
+                            s2[e] = a * a;
+                        }
                     }
 #pragma unroll
                     for (int w = 8; w >= 1; w >>= 1) {            // lane mask 16, 8, 4, 2 <-> keep 8, 4, 2, 1 columns
@@ -556,16 +603,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
                     s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
                     const int col = cc + (lane >> 1);             // lane bits 4..1 = column within the 16-column group
-                    if ((lane & 1) == 0 && col < p.Cout) {
+                    if ((lane & 1) == 0 && nt * n_tile + col < p.Cout) {
                         atomicAdd(&s_stat[col], s1[0]);
                         atomicAdd(&s_stat[MAX_N + col], s2[0]);
                     }
                 }
             }
+            if (p.stat_sum && p.n_tiles > 1) {
+                // several N tiles per layer (1x1 dgrads onto wide slabs): the per-CTA partials belong to THIS tile's channel
+                // range -- flush them before the next tile (four epilogue warps only)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = (int)threadIdx.x - (NUM_THREADS - EPI_THREADS); c < n_tile; c += EPI_THREADS) {
+                    const int ch = nt * n_tile + c;
+                    if (ch < p.Cout) {
+                        atomicAdd(p.stat_sum + ch, (double)s_stat[c]);
+                        atomicAdd(p.stat_sumsq + ch, (double)s_stat[MAX_N + c]);
+                    }
+                    s_stat[c] = 0.f;
+                    s_stat[MAX_N + c] = 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             tc_fence_before();
             mbar_arrive(tmem_empty(acc));        // this thread is done reading the accumulator
         }
-        if (p.stat_sum) {
+        if (p.stat_sum && p.n_tiles == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
             for (int c = (int)threadIdx.x - (NUM_THREADS - EPI_THREADS); c < p.Cout; c += EPI_THREADS) {
                 atomicAdd(p.stat_sum + c, (double)s_stat[c]);
@@ -657,12 +719,16 @@ extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, lon
     return 0;
 }
 
+struct BnBwdArgs {
+    const float *x; long long xs; const float *st; int relu;
+};
+
 static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int upsample2, int out_h,
                          int out_w, int kwin, int Cin,
                          int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                          const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
                          long long out_pixel_stride, int act, int precision, double *stat_sum, double *stat_sumsq,
-                         void *stream) {
+                         void *stream, const BnBwdArgs *bnb = nullptr) {
     if (!x || !wpack || !out || B < 0 || Hs < 1 || Ws < 1 || Cin < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 ||
         pad < 0 || dil < 1)
         return BTS_EINVAL;
@@ -687,7 +753,13 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     p.out = out; p.os = out_pixel_stride; p.act = act; p.precision = precision;
     p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
     if ((stat_sum == nullptr) != (stat_sumsq == nullptr)) return BTS_EINVAL;
-    if (stat_sum && (p.n_tiles != 1 || act != 0)) return BTS_EINVAL;   // epilogue statistics: one N tile (Cout <= 256), no activation
+    p.bnb_x = nullptr; p.bnb_xs = 0; p.bnb_st = nullptr; p.bnb_relu = 0;
+    if (bnb) {
+        if (!bnb->x || !bnb->st || !stat_sum || act != 0) return BTS_EINVAL;
+        p.bnb_x = bnb->x; p.bnb_xs = bnb->xs; p.bnb_st = bnb->st; p.bnb_relu = bnb->relu ? 1 : 0;
+    }
+    if (stat_sum && act != 0) return BTS_EINVAL;                        // statistics of the raw conv output only
+    if (stat_sum && !bnb && p.n_tiles != 1) return BTS_EINVAL;          // forward statistics: one N tile (Cout <= 256)
     const int Hin = p.up ? 2 * Hs : Hs, Win = p.up ? 2 * Ws : Ws;
     p.Hv = Hin; p.Wv = Win;      // mode 2: live source coordinates are the even ones below 2Hs x 2Ws, zeros everywhere else
     p.Hout = p.up == 2 ? out_h : (Hin + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
@@ -794,4 +866,19 @@ extern "C" int bts_conv_pack_weights_multi(const void *descs, int n, long long t
     pack_weights_multi_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackDesc *>(descs), n, total);
     BTS_LAUNCH_CHECK();
     return 0;
+}
+
+// dgrad whose epilogue also reduces the BatchNorm(+ReLU) backward sums of the layer in front of the conv: the tile written
+// is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat with mask = [bn(x)>0] (relu) or 1,
+// xhat = (x - mean)*invstd.  x_bn: the BatchNorm INPUT at the output's pixels/channels (NHWC, pixel stride x_bn_stride),
+// bn_st: [4][Cout] = scale, shift, mean, invstd (bts_bn_finalize layout).  S1/S2 must be zeroed.  Replaces the separate
+// bts_bn_relu_bwd_reduce pass over (x, g) -- 174 launches and two full tensor reads per DenseNet-161 step.
+extern "C" int bts_conv_fwd_bnbwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int source_mode, int out_h,
+                                  int out_w, int kwin, int Cin, int KH, int KW, int stride, int pad, int dil,
+                                  const float *wpack, int Cout, float *out, long long out_pixel_stride, int precision,
+                                  const float *x_bn, long long x_bn_stride, const float *bn_st, int relu, double *S1,
+                                  double *S2, void *stream) {
+    BnBwdArgs a{x_bn, x_bn_stride, bn_st, relu};
+    return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, source_mode, out_h, out_w, kwin, Cin, KH, KW, stride, pad, dil, wpack,
+                         Cout, nullptr, nullptr, 0, out, out_pixel_stride, 0, precision, S1, S2, stream, &a);
 }

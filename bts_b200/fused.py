@@ -86,6 +86,42 @@ def bn_relu_backward(x, g, st, use_stats, out, accumulate):
     return S
 
 
+EPI_BNBWD = True    # BatchNorm-backward sums reduced in the dgrad epilogue (bts_conv_fwd_bnbwd) instead of a separate pass
+
+
+def bn_relu_backward_from_sums(x, g, st, S, use_stats, out, accumulate):
+    """the apply half of bn_relu_backward when S = (S1, S2) already came out of the dgrad epilogue"""
+    x, xs = _view(x)
+    g, gs = _view(g)
+    out, os_ = _view(out)
+    B, C, H, W = x.shape
+    M = B * H * W
+    L = _lib.lib()
+    coef = None
+    if use_stats:
+        coef = torch.empty((2, C), device=x.device, dtype=torch.float32)
+        _lib.check(L.bts_bn_bwd_coef(_ptr(S[0]), _ptr(S[1]), M, C, _ptr(st[0]), _ptr(st[2]), _ptr(st[3]), _ptr(coef), _stream()),
+                   "bts_bn_bwd_coef")
+    _lib.check(L.bts_bn_relu_bwd_apply(_ptr(x), xs, _ptr(g), gs, M, C, _ptr(st[0]), _ptr(st[1]), _ptr(coef), _ptr(out), os_,
+                                       int(accumulate), _stream()), "bts_bn_relu_bwd_apply")
+    _lib.count(2)
+    return S
+
+
+def dgrad_bn_relu_backward(gy, weight, padding, dilation, x_bn, st, use_stats, out=None, accumulate=False):
+    """d/dx_bn of conv(relu(bn(x_bn))) given gy = d/d(conv output): dgrad on the engine with the BatchNorm-backward sums
+    reduced in its epilogue, then one streaming apply pass.  Returns (dx, S) with S = (dbeta, dgamma) as fp64 [2,C]."""
+    KH = weight.shape[2]
+    C = weight.shape[1]
+    S = torch.zeros((2, C), device=gy.device, dtype=torch.float64)
+    g_a = conv.conv2d_tc(gy, weight, 1, dilation * (KH - 1) - padding, dilation, transpose_flip=True, stats=S,
+                         bn_bwd=(x_bn, st, True))
+    if out is None:
+        out = g_a
+    bn_relu_backward_from_sums(x_bn, g_a, st, S, use_stats, out, accumulate)
+    return out, S
+
+
 class _DenseBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, block, training, *params):
@@ -143,9 +179,12 @@ class _DenseBlockFn(torch.autograd.Function):
             if need[6 * li + 5]:
                 grads[6 * li + 5] = conv.wgrad_tc(b, g_out, w2.shape, w2.stride(), 1, 1, 1, pre_scale=st2[0],
                                                   pre_shift=st2[1], pre_relu=True)
-            g_a2 = conv.conv2d_tc(g_out, w2, 1, 1, 1, transpose_flip=True)
-            # ---- norm2 + relu2 backward (in place on g_a2)
-            S = bn_relu_backward(b, g_a2, st2, training, g_a2, False)
+            if EPI_BNBWD:
+                g_a2, S = dgrad_bn_relu_backward(g_out, w2, 1, 1, b, st2, training)        # sums in the dgrad epilogue
+            else:
+                g_a2 = conv.conv2d_tc(g_out, w2, 1, 1, 1, transpose_flip=True)
+                # ---- norm2 + relu2 backward (in place on g_a2)
+                S = bn_relu_backward(b, g_a2, st2, training, g_a2, False)
             if need[6 * li + 3]:
                 grads[6 * li + 3] = S[1].float()
             if need[6 * li + 4]:
@@ -155,9 +194,12 @@ class _DenseBlockFn(torch.autograd.Function):
             if need[6 * li + 2]:
                 grads[6 * li + 2] = conv.wgrad_tc(xin, g_a2, w1.shape, w1.stride(), 1, 0, 1, pre_scale=st1[0],
                                                   pre_shift=st1[1], pre_relu=True)
-            g_a1 = conv.conv2d_tc(g_a2, w1, 1, 0, 1, transpose_flip=True)
             # ---- norm1 + relu1 backward, accumulated into the gradient slab (the concat fan-out)
-            S = bn_relu_backward(xin, g_a1, st1, training, G[:, :C], True)
+            if EPI_BNBWD:
+                _, S = dgrad_bn_relu_backward(g_a2, w1, 0, 1, xin, st1, training, out=G[:, :C], accumulate=True)
+            else:
+                g_a1 = conv.conv2d_tc(g_a2, w1, 1, 0, 1, transpose_flip=True)
+                S = bn_relu_backward(xin, g_a1, st1, training, G[:, :C], True)
             if need[6 * li + 0]:
                 grads[6 * li + 0] = S[1].float()
             if need[6 * li + 1]:

@@ -215,8 +215,12 @@ class _BnReluConv(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             gw = conv.wgrad_tc(x, gy, weight.shape, weight.stride(), 1, padding, dilation, pre_scale=st[0], pre_shift=st[1],
                                pre_relu=True)
-        g_a = conv.conv2d_tc(gy, weight, 1, dilation * (KH - 1) - padding, dilation, transpose_flip=True)
-        gx, S = bn_backward(x, g_a, st, batch, True, out=g_a)          # in place on the dgrad result
+        from . import fused
+        if fused.EPI_BNBWD:
+            gx, S = fused.dgrad_bn_relu_backward(gy, weight, padding, dilation, x, st, batch)   # sums in the dgrad epilogue
+        else:
+            g_a = conv.conv2d_tc(gy, weight, 1, dilation * (KH - 1) - padding, dilation, transpose_flip=True)
+            gx, S = bn_backward(x, g_a, st, batch, True, out=g_a)          # in place on the dgrad result
         return (gx if ctx.needs_input_grad[0] else None, S[1].float() if ctx.needs_input_grad[1] else None,
                 S[0].float() if ctx.needs_input_grad[2] else None, gw, None, None, None)
 

@@ -130,6 +130,16 @@ int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, int Hs, int
                     int kwin, int Cin, int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                     const float *pre_scale, const float *pre_shift, int pre_relu, float *out, long long out_pixel_stride,
                     int act, int precision, double *stat_sum, double *stat_sumsq, void *stream);
+/* dgrad (or any act-free conv) whose epilogue also reduces the BatchNorm(+ReLU)-backward sums of the layer in front of the
+ * conv: the tile written is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat (zero them first),
+ * mask = [bn(x)>0] when relu else 1, xhat = (x-mean)*invstd; bn_st = [4][Cout] scale|shift|mean|invstd.  Replaces the
+ * bts_bn_bwd_reduce pass over (x, g); follow with bts_bn_bwd_coef + bts_bn_bwd_apply. */
+int bts_conv_fwd_bnbwd(const float *x, long long x_pixel_stride, int B, int Hs, int Ws, int source_mode, int out_h, int out_w,
+                       int kwin, int Cin, int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
+                       float *out, long long out_pixel_stride, int precision, const float *x_bn, long long x_bn_stride,
+                       const float *bn_st, int relu, double *S1, double *S2, void *stream);
+int bts_bn_bwd_coef(const double *S1, const double *S2, long long M, int C, const float *scale, const float *mean,
+                    const float *invstd, float *coef, void *stream);
 /* grouped 3x3 (ResNeXt: 32 groups of cpg channels): w is (width, cpg, KH, KW).  bts_conv_group_window -> the diagonal block
  * width kwin the packed operator uses (128 when width % 128 == 0 and 128 % cpg == 0; 0 = not supported). */
 int bts_conv_group_window(int width, int cpg);
