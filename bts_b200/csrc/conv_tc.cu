@@ -216,10 +216,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     float *s_shift = s_scale + p.KC * 32;
     const uint32_t bar_off = pre_off + (PRE >= 2 ? (uint32_t)p.KC * 32u * 8u : 0u);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + bar_off);
-    // bars: [0..MS) full_a, [MS..2MS) full_b, [2MS..3MS) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base word
+    // bars: [0..MS) full (128 producer arrivals + the weight loader's expect_tx arrival + its bytes), [2MS..3MS) empty, then
+    // tmem_full[2], tmem_empty[2]; then the TMEM base word
     const uint32_t bar0 = base + bar_off;
     auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto full_b = full_a;                  // ONE barrier per stage: the MMA warp pays one try_wait per k-block, not two
     auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
     auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
@@ -237,8 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_a(s), PRODUCER_THREADS);
-            mbar_init(full_b(s), 1);
+            mbar_init(full_a(s), PRODUCER_THREADS + 1);
             mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -279,58 +279,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            // Instruction-count economy (measured, round 1): a tcgen05.mma with M=128, K=8 (tf32) costs ~115-130 cycles
-            // whatever N is -- fetching the 128 A rows from shared memory sets the pace -- so every layer ran at ~1400
-            // cycles per k-block (12 MMAs) regardless of Cout, load latency or producer instruction count.  Hence:
-            //   * n_tile <= 128: B_hi and B_lo are adjacent in the stage, so ONE instruction with N = 2*n_tile computes
-            //     A_hi*[B_hi;B_lo] into 2*n_tile accumulator columns (the epilogue adds the two halves); the third
-            //     product A_lo*B_hi is a second instruction: 2 MMAs per k-step instead of 3;
-            //   * n_tile <= 256 is one tile (3 MMAs per k-step, the activation tile produced once) instead of two tiles.
-            const bool stack = n_tile <= 128;
-            const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
-            const uint32_t idesc2 = make_idesc(BLOCK_M, 2 * n_tile);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int acc = ti & 1;
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        // Instruction-count economy, part 2 (round 2; ncu source view of the round-1 kernel, profiles/r01_conv_db1_3x3_v4):
+        // the issuing warp executed ~300 instructions per k-block -- two try_waits, four 64-bit descriptors rebuilt from
+        // addresses, per-MMA predicate set-up and the ELECT / BRA.U.ANY uniformity loops the compiler wraps around every
+        // uniform-datapath instruction inside a divergent `if (lane == 0)` -- at ~4 cycles each: ~1300 cycles per k-block
+        // WHATEVER N is; the tensor pipe itself was busy 39 cycles per MMA (= N/256 * 128, the hardware floor).  Hence:
+        //   * the whole warp runs the loop (warp-uniform control flow), one elected lane issues;
+        //   * one `full` barrier per stage; descriptors advance by adding constants to stage-0 descriptors;
+        //   * the precision / stacking mode is resolved outside the tile loop.
+        // MMA count economy of round 1 is kept: n_tile <= 128 -> A_hi*[B_hi;B_lo] is ONE instruction of width 2*n_tile
+        // (+ A_lo*B_hi): 2 MMAs per k-step; wider tiles: 3 MMAs per k-step over one 256-wide tile.
+        const bool stack = n_tile <= 128;
+        const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
+        const uint32_t idesc2 = make_idesc(BLOCK_M, 2 * n_tile);
+        const uint64_t dA0 = make_desc(base);                                  // A_hi of stage 0
+        const uint64_t oAlo = (uint64_t)(A_TILE_BYTES >> 4), oBhi = (uint64_t)((2 * A_TILE_BYTES) >> 4);
+        const uint64_t oBlo = oBhi + (uint64_t)((n_tile * 128) >> 4), stage_step = (uint64_t)(stage_bytes >> 4);
+        const int mode = p.precision != 0 ? 2 : (stack ? 0 : 1);
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        uint64_t d = dA0;
+        uint32_t bfull = full_a(0), bempty = empty(0);
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int acc = ti & 1;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+            mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bfull, ph);
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(full_a(s), ph);
-                    mbar_wait(full_b(s), ph);
-                    tc_fence_after();
-                    const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
-                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
-                    const uint32_t b_lo = b_hi + n_tile * 128;
-                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
-                    if (p.precision == 0) {
-                        if (stack) {
+                if (leader) {
+                    const uint64_t dah = d, dal = d + oAlo, dbh = d + oBhi, dbl = d + oBlo;
+                    const uint32_t first = kb != 0;
+                    if (mode == 0) {
+                        umma_tf32(d_tmem, dah, dbh, idesc2, first);          // A_hi * [B_hi ; B_lo]
+                        umma_tf32(d_tmem, dal, dbh, idesc, 1);               // A_lo * B_hi
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 8; ++k) {
-                                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc2, (kb | k) != 0);   // A_hi * [B_hi ; B_lo]
-                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);                // A_lo * B_hi
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
-                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
-#pragma unroll
-                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                        for (int k = 1; k < BLOCK_K / 8; ++k) {
+                            umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc2, 1);
+                            umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
                         }
-                    } else {
+                    } else if (mode == 1) {
+                        umma_tf32(d_tmem, dal, dbh, idesc, first);           // small cross terms first
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 8; ++k)
-                            umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 1; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                    } else {
+                        umma_tf32(d_tmem, dah, dbh, idesc, first);
+#pragma unroll
+                        for (int k = 1; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
                     }
-                    umma_commit(empty(s));       // frees the stage when these MMAs have read it
-                    if (++s == S) { s = 0; ph ^= 1; }
+                    umma_commit(bempty);         // frees the stage when these MMAs have read it
+                    if (kb == KB - 1) umma_commit(tmem_full(acc));     // accumulator of this tile complete
                 }
-                umma_commit(tmem_full(acc));     // accumulator of this tile complete
+                __syncwarp();
+                d += stage_step; bfull += 8u; bempty += 8u;
+                if (++s == S) { s = 0; ph ^= 1; d = dA0; bfull = full_a(0); bempty = empty(0); }
             }
         }
     } else if (warp < 10) {

@@ -102,41 +102,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 1) {
-        if (lane == 0) {
-            // 2 MMAs per k-group instead of 3 (a tcgen05.mma with M=128, K=8 costs ~120 cycles whatever N is): the dY_lo
-            // chunks follow the dY_hi chunks in the stage, so one instruction with N = 32*nchunk + n_tile computes
-            // x_hi^T * [dY_hi ; dY_lo]; the epilogue adds the column blocks [0,n_tile) and [32*nchunk, 32*nchunk+n_tile).
-            const int nchunk_b = (n_tile + 31) >> 5;
-            const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
-            const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
-            const bool stack = n_tile <= 128;          // wider tiles: three plain products per k-group
-            int s = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < nkb; ++it) {
-                mbar_wait(full(s), ph);
-                tc_fence_after();
-                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + (uint32_t)nchunk_b * CHUNK_BYTES;
+        // MMA issuer.  Whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers and
+        // lets the compiler emit back-to-back UTCHMMA); one elected lane issues.  Descriptors advance by constants -- the
+        // round-1 loop rebuilt 16 descriptors per k-block from addresses and paid ~300 issue-warp instructions per
+        // k-block (see conv_tc.cu), which is what held every wgrad layer at 2.2-3.7x its MMA bound.
+        // 2 MMAs per k-group instead of 3: the dY_lo chunks follow the dY_hi chunks in the stage, so one instruction with
+        // N = 32*nchunk + n_tile computes x_hi^T * [dY_hi ; dY_lo]; the epilogue adds the column blocks [0,n_tile) and
+        // [32*nchunk, 32*nchunk+n_tile).  Wider tiles (n_tile > 128): three plain products per k-group.
+        const int nchunk_b = (n_tile + 31) >> 5;
+        const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
+        const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
+        const int mode = p.precision != 0 ? 2 : (n_tile <= 128 ? 0 : 1);
+        const uint64_t dA0 = make_desc_mn(base, CHUNK_BYTES);                     // x_hi of stage 0, k-group 0
+        const uint64_t oAlo = (uint64_t)(A_BYTES >> 4), oBhi = (uint64_t)((2 * A_BYTES) >> 4);
+        const uint64_t oBlo = oBhi + (uint64_t)((nchunk_b * CHUNK_BYTES) >> 4), stage_step = (uint64_t)(stage_bytes >> 4);
+        constexpr uint64_t KG = 1024 >> 4;                                         // one k-group = 8 pixel rows = 1024 B
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        uint64_t d = dA0;
+        uint32_t bfull = full(0), bempty = empty(0);
+        for (int it = 0; it < nkb; ++it) {
+            mbar_wait(bfull, ph);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t dah = d, dal = d + oAlo, dbh = d + oBhi, dbl = d + oBlo;
+                const uint32_t first = it != 0;
+                if (mode == 0) {
+                    umma_tf32(tmem_base, dah, dbh, idesc2, first);                // x_hi * [dY_hi ; dY_lo]
+                    umma_tf32(tmem_base, dal, dbh, idesc, 1);                     // x_lo * dY_hi
 #pragma unroll
-                for (int kg = 0; kg < BLOCK_KP / 8; ++kg) {
-                    const uint64_t dah = make_desc_mn(a_hi + kg * 1024, CHUNK_BYTES), dal = make_desc_mn(a_lo + kg * 1024, CHUNK_BYTES);
-                    const uint64_t dbh = make_desc_mn(b_hi + kg * 1024, CHUNK_BYTES), dbl = make_desc_mn(b_lo + kg * 1024, CHUNK_BYTES);
-                    if (p.precision == 0 && stack) {
-                        umma_tf32(tmem_base, dah, dbh, idesc2, (it | kg) != 0);   // x_hi * [dY_hi ; dY_lo]
-                        umma_tf32(tmem_base, dal, dbh, idesc, 1);                 // x_lo * dY_hi
-                    } else if (p.precision == 0) {
-                        umma_tf32(tmem_base, dal, dbh, idesc, (it | kg) != 0);
-                        umma_tf32(tmem_base, dah, dbl, idesc, 1);
-                        umma_tf32(tmem_base, dah, dbh, idesc, 1);
-                    } else {
-                        umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
+                    for (int kg = 1; kg < BLOCK_KP / 8; ++kg) {
+                        umma_tf32(tmem_base, dah + kg * KG, dbh + kg * KG, idesc2, 1);
+                        umma_tf32(tmem_base, dal + kg * KG, dbh + kg * KG, idesc, 1);
                     }
+                } else if (mode == 1) {
+                    umma_tf32(tmem_base, dal, dbh, idesc, first);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1);
+                    umma_tf32(tmem_base, dah, dbh, idesc, 1);
+#pragma unroll
+                    for (int kg = 1; kg < BLOCK_KP / 8; ++kg) {
+                        umma_tf32(tmem_base, dal + kg * KG, dbh + kg * KG, idesc, 1);
+                        umma_tf32(tmem_base, dah + kg * KG, dbl + kg * KG, idesc, 1);
+                        umma_tf32(tmem_base, dah + kg * KG, dbh + kg * KG, idesc, 1);
+                    }
+                } else {
+                    umma_tf32(tmem_base, dah, dbh, idesc, first);
+#pragma unroll
+                    for (int kg = 1; kg < BLOCK_KP / 8; ++kg) umma_tf32(tmem_base, dah + kg * KG, dbh + kg * KG, idesc, 1);
                 }
-                umma_commit(empty(s));
-                if (++s == S) { s = 0; ph ^= 1; }
+                umma_commit(bempty);
+                if (it == nkb - 1) umma_commit(accum_full);
             }
-            umma_commit(accum_full);
+            __syncwarp();
+            d += stage_step; bfull += 8u; bempty += 8u;
+            if (++s == S) { s = 0; ph ^= 1; d = dA0; bfull = full(0); bempty = empty(0); }
         }
+        if (nkb == 0 && leader) umma_commit(accum_full);      // empty split: release the epilogue (it writes zeros)
     } else if (warp >= 2) {
         // 8 warps per group (round 1 ran 4 with two pixel rows per thread: ~9 cycles between a warp's instructions at
         // 2.5 warps per scheduler made the producers, not the tensor pipe, set the k-block time): one pixel row of the
