@@ -568,18 +568,38 @@ def _run_ours(args):
     himg, hfocal, hgt = synth_batch(cfg, B, 1 + rank, pin=True)
     total_steps = 10000
 
+    graphed = None
+    graph_note = "off"
+    if train and args.graph != "off" and args.reducer != "ddp":
+        # forward + loss + backward of one step as ONE CUDA graph (bts_b200/graph.py); collective + optimizer stay eager
+        try:
+            from bts_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(model, lambda out, g: crit(out[4], g, g > cfg["thr"]), ((img, focal), (gt,)))
+            graph_note = "fwd+loss+bwd captured in one CUDA graph (%d native launches per replay)" % graphed.launches_per_replay
+        except Exception as e:
+            if args.graph == "on":
+                raise
+            graphed = None
+            graph_note = "capture failed (%s: %s) -> eager launches" % (type(e).__name__, str(e)[:120])
+            for q in model.parameters():
+                q.grad = None
+            torch.cuda.synchronize()
+
     def step(i, x, f, g):
         if not train:
             with torch.no_grad():
                 return model(x, f)[4].sum()
-        opt.zero_grad()
         if bcast is not None:
             bcast.broadcast(0)
-        out = model(x, f)
-        loss = crit(out[4], g, g > cfg["thr"])
-        loss.backward()
+        if graphed is not None:
+            loss = graphed((x, f), (g,))
+        else:
+            opt.zero_grad()
+            out = model(x, f)
+            loss = crit(out[4], g, g > cfg["thr"])
+            loss.backward()
         if red is not None:
-            red.reduce()
+            red.reduce(inplace=graphed is not None)
         lr = (1e-4 - 1e-5) * (1 - i / total_steps) ** 0.9 + 1e-5
         for grp in opt.param_groups:
             grp["lr"] = lr
@@ -616,6 +636,8 @@ def _run_ours(args):
     ms, launches, clocks, per = timed(lambda i: step(i, img, focal, gt), K, Wm)
 
     def e2e_step(i):
+        if graphed is not None:                  # H2D straight into the graph's static input buffers
+            return float(step(i, himg, hfocal, hgt).detach())
         x = himg.to(dev, non_blocking=True)
         f = hfocal.to(dev, non_blocking=True)
         g = hgt.to(dev, non_blocking=True)
@@ -635,6 +657,7 @@ def _run_ours(args):
                                    "one NCCL all-reduce (AVG) of the flat gradient vector per step + one flat buffer broadcast")),
                    "l2": "no explicit flush: per-step working set (saved activations, GBs) >> 126 MB L2",
                    "precision": "3xTF32 split on tcgen05 (fp32-grade, parity mode)",
+                   "cuda_graph": graph_note,
                    "optimizer": ("bts_b200.optim.FusedAdamW (one multi-tensor kernel + one re-pack launch)"
                                  if args.optimizer == "fused" else "torch.optim.AdamW") if train else "none"},
         "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
@@ -659,7 +682,12 @@ def _run_ours(args):
                                         peak_note="parity-grade 3xTF32 = TF32 GEMM peak measured live (sustained) / 3")
             if train:
                 try:
-                    rl = conv_rooflines(torch, conv, lambda: step(Wm + K, img, focal, gt), live)
+                    def eager_step():                       # the traced step runs eagerly (CUDA events around every call)
+                        for q in model.parameters():
+                            q.grad = None
+                        o = model(img, focal)
+                        crit(o[4], gt, gt > cfg["thr"]).backward()
+                    rl = conv_rooflines(torch, conv, eager_step, live)
                     if "conv" in rl:
                         res["roofline"] = dict(rl["conv"], kernel="conv_tc_kernel (tcgen05 implicit GEMM: every conv forward and "
                                                                   "dgrad of the step), all launches of one real training step",
@@ -716,6 +744,8 @@ def main():
                     help="N>1: flat = one all-reduce of the flat gradient vector (bts_b200/dist.py); ddp = torch DDP as bts_main.py")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="fused = bts_b200.optim.FusedAdamW (default), torch = torch.optim.AdamW exactly as bts_main.py")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="capture fwd+loss+bwd of the train step in one CUDA graph (auto: fall back to eager if capture fails)")
     ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager/cuDNN reference leg")

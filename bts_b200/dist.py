@@ -47,7 +47,9 @@ class FlatGradReducer:
             o += p.numel()
 
     @torch.no_grad()
-    def reduce(self):
+    def reduce(self, inplace=False):
+        """inplace=False: afterwards p.grad IS the reduced flat view (no copy back).  inplace=True: the averaged values are
+        copied back into the existing .grad tensors -- for static gradients of a CUDA-graphed step (bts_b200.graph)."""
         world = dist.get_world_size(self.group)
         src, dst, missing = [], [], []
         for p, v in zip(self.params, self.views):
@@ -64,6 +66,12 @@ class FlatGradReducer:
         dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group)
         if not avg:
             self.flat.div_(world)
+        if inplace and dst:
+            torch._foreach_copy_(src, dst)
+            for p, v in zip(self.params, self.views):
+                if p.grad is None:
+                    p.grad = v
+            return
         for p, v in zip(self.params, self.views):
             p.grad = v                                       # the optimizer reads the reduced flat buffer in place
 
