@@ -35,6 +35,9 @@
 //                 accumulator back to the MMA warp.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>
 
 #include "tc_common.cuh"
 
@@ -81,6 +84,8 @@ struct ConvParams {
     double *stat_sum, *stat_sumsq;   // optional per-output-channel sum / sum of squares of the (activated) output
     // BatchNorm-backward reduction fused into a dgrad's epilogue (bnb_x != null): the tile being written is g = dL/d relu(bn(x));
     // stat_sum[c] += sum_p g*[bn(x)>0],  stat_sumsq[c] += sum_p g*[bn(x)>0]*xhat   (bts_bn_relu_bwd_reduce without its pass)
+    int tma_adj;             // TMA mode: base-pixel coordinate = out*stride - tma_adj (the bounding box's lower corner)
+    tc::FastDiv fd_kc;       // TMA mode: k-block -> (tap, 32-channel chunk) = (kb / KC, kb % KC)
     const float *bnb_x; long long bnb_xs;
     const float *bnb_st;             // [4][Cout]: scale, shift, mean, invstd
     int bnb_relu;
@@ -203,8 +208,15 @@ constexpr int STAT_BYTES = 2 * MAX_N * 4;   // per-CTA fp32 partial sums of the 
 //   * the per-tile pixel decode uses multiply-shift division by host-precomputed constants (FastDiv);
 //   * long waits (epilogue on the accumulator, weight loader on a free stage) back off with nanosleep so the spinning
 //     warps stop competing with the producers for issue slots.
-template <int PRE, int UP, bool VEC>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p) {
+// TMA = true: the activation tile is staged by the Tensor Memory Accelerator (one cp.async.bulk.tensor im2col load per
+// k-block lands 128 pixels x 32 channels, swizzled, zero-filled where the filter tap falls into the padding) and is used
+// AS IS as the A_hi operand (the tensor core reads the top 19 bits of each fp32 word); the producer warps only derive
+// A_lo = x - trunc_tf32(x) from shared memory (and apply the BN/ReLU pre-op in place) -- no global loads, no address /
+// bounds arithmetic, one shared store instead of two: ~2.8x fewer producer instructions per k-block.  K is enumerated per
+// tap in 32-channel chunks (identical to the dense-quad order whenever the K channels are a multiple of 32, which the
+// host requires), stride 1, no up-sample.
+template <int PRE, int UP, bool VEC, bool TMA>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -220,7 +232,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     // tmem_full[2], tmem_empty[2]; then the TMEM base word
     const uint32_t bar0 = base + bar_off;
     auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = full_a;                  // ONE barrier per stage: the MMA warp pays one try_wait per k-block, not two
+    // ONE barrier per stage for the MMA warp (one try_wait per k-block).  TMA mode adds `raw` barriers for the loads:
+    // TMA bytes (A raw tile + weights) land on raw(s), the lo-producers wait there and then arrive on full(s).
+    auto raw = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto full_b = [&](int s) { return TMA ? raw(s) : full_a(s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
     auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
@@ -238,7 +253,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_a(s), PRODUCER_THREADS + 1);
+            mbar_init(full_a(s), TMA ? PRODUCER_THREADS : PRODUCER_THREADS + 1);
+            mbar_init(raw(s), 1);
             mbar_init(empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -263,15 +279,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ===================== weight loader =====================
         if (lane == 0) {
             const uint32_t bytes = 2u * (uint32_t)n_tile * 128u;
+            if (TMA) tma_prefetch_desc(&tmap);
             int s = 0;
             uint32_t ph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int nt = tile - (int)fdiv((uint32_t)tile, p.fd_ntiles) * p.n_tiles;
+                const uint32_t m_tile = fdiv((uint32_t)tile, p.fd_ntiles);
+                const int nt = tile - (int)m_tile * p.n_tiles;
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) + (size_t)nt * KB * bytes;
+                int tw = 0, th = 0, tn = 0;
+                if (TMA) {                         // first output pixel of the tile -> base-pixel coordinate of the im2col walk
+                    const uint32_t m0 = m_tile * BLOCK_M;
+                    const uint32_t q = fdiv(m0, p.fd_wout);
+                    const uint32_t b = fdiv(q, p.fd_hout);
+                    tw = (int)(m0 - q * (uint32_t)p.Wout) - p.tma_adj;
+                    th = (int)(q - b * (uint32_t)p.Hout) - p.tma_adj;
+                    tn = (int)b;
+                }
+                int tap = 0, kc = 0;               // k-block -> (tap, chunk), advanced incrementally
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait_sleep(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full_b(s), bytes);
+                    if (TMA) {
+                        mbar_arrive_expect_tx(raw(s), bytes + (uint32_t)A_TILE_BYTES);
+                        const int ky = (int)fdiv((uint32_t)tap, p.fd_kw), kx = tap - ky * p.KW;
+                        tma_im2col_4d(base + (uint32_t)s * stage_bytes, &tmap, nt * p.kwin + kc * 32, tw, th, tn, raw(s),
+                                      (uint16_t)(kx * p.dil), (uint16_t)(ky * p.dil));
+                        if (++kc == p.KC) { kc = 0; ++tap; }
+                    } else {
+                        mbar_arrive_expect_tx(full_b(s), bytes);
+                    }
                     bulk_copy_g2s(base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES, src + (size_t)kb * bytes, bytes, full_b(s));
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
@@ -357,6 +393,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         const float *__restrict__ xg = p.x;
         // swizzled byte offset of (row r0 + 16 i, chunk) inside a tile = roff0 + i * 2048
         const uint32_t roff0 = (uint32_t)r0 * 128u + (uint32_t)((chunk ^ (r0 & 7)) << 4);
+        if constexpr (TMA) {
+            // ---- lo-producers: the raw tile is already in shared memory (TMA); derive A_lo (and the pre-op) in place
+            const bool need_mask = AFF && taps > 1;        // zero padding is applied AFTER the BatchNorm/ReLU pre-op
+            int oyt[8], oxt[8];
+            int ti = 0, kb = grp, cur = -1;
+            while (kb >= KB) { kb -= KB; ++ti; }
+            int s_t = grp;
+            uint32_t ph_t = 0;
+            const int mine_t = (total_kb - grp + 1) >> 1;
+            for (int it = 0; it < mine_t; ++it) {
+                int tap = 0, kc = kb;
+                if (taps > 1) { tap = (int)fdiv((uint32_t)kb, p.fd_kc); kc = kb - tap * p.KC; }
+                const int c = kc * 32 + chunk * 4;
+                uint32_t live = 0xffu;
+                if (need_mask) {
+                    if (ti != cur) {
+                        cur = ti;
+                        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                        const uint32_t m_base = fdiv((uint32_t)tile, p.fd_ntiles) * BLOCK_M + (uint32_t)r0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t m = m_base + 16u * i;
+                            const uint32_t q = fdiv(m, p.fd_wout);
+                            const uint32_t b = fdiv(q, p.fd_hout);
+                            oxt[i] = (int)(m - q * (uint32_t)p.Wout) - p.pad;
+                            oyt[i] = (int)(q - b * (uint32_t)p.Hout) - p.pad;
+                        }
+                    }
+                    const int ky = (int)fdiv((uint32_t)tap, p.fd_kw), kx = tap - ky * KW;
+                    live = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        live |= (((unsigned)(oyt[i] + ky * dil) < (unsigned)Hin && (unsigned)(oxt[i] + kx * dil) < (unsigned)Win) ? 1u : 0u) << i;
+                }
+                float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+                if (AFF) {
+                    const float4 a4 = *reinterpret_cast<const float4 *>(s_scale + c);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_shift + c);
+                    sc[0] = a4.x; sc[1] = a4.y; sc[2] = a4.z; sc[3] = a4.w;
+                    sh[0] = b4.x; sh[1] = b4.y; sh[2] = b4.z; sh[3] = b4.w;
+                }
+                const uint32_t a_hi = base + (uint32_t)s_t * stage_bytes + roff0;
+                const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                mbar_wait(raw(s_t), ph_t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 q4 = ld_shared_v4(a_hi + (uint32_t)i * 2048u);
+                    float v[4] = {q4.x, q4.y, q4.z, q4.w}, lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = v[e];
+                        if (AFF) {
+                            a = fmaf(a, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
+                            if (RELU) a = fmaxf(a, 0.f);
+                            a = ((live >> i) & 1u) ? a : 0.f;
+                        } else if (RELU) {
+                            a = fmaxf(a, 0.f);
+                        }
+                        v[e] = a;
+                        lo[e] = a - __uint_as_float(__float_as_uint(a) & 0xffffe000u);   // exact; hi = what the tensor core reads
+                    }
+                    if (PRE != 0) st_shared_v4(a_hi + (uint32_t)i * 2048u, v[0], v[1], v[2], v[3]);
+                    st_shared_v4(a_lo + (uint32_t)i * 2048u, lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_proxy_async();
+                mbar_arrive(full_a(s_t));
+                s_t += 2;
+                if (s_t >= S) { s_t -= S; ph_t ^= 1; }
+                kb += 2;
+                while (kb >= KB) { kb -= KB; ++ti; }
+            }
+        } else {
         // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block this group loads; this lane's channel
         //      quad of that k-block is g = 8 kb + chunk -> (tap, quad in tap) by multiply-shift division
         int oy[8], ox[8], rowoff[8];
@@ -493,6 +601,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 }
             }
         }
+        }   // !TMA
     } else {
         // ===================== epilogue warps (10..13) =====================
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
@@ -727,6 +836,52 @@ extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, lon
     return 0;
 }
 
+// ---- TMA tensor map of the NHWC activation tensor, im2col mode (cuTensorMapEncodeIm2col through the runtime's driver
+//      entry-point query: no link-time dependency on libcuda)
+static int g_tma_mode = 0;      // 0 off, 1 on, 2 on with base-pixel coordinates NOT shifted by the lower corner, 3 on + strict
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn encode_im2col_fn() {
+    static EncodeIm2colFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+    }
+    return fn;
+}
+
+// x: NHWC fp32, pixel stride xs floats (a channel slice of a wider slab is fine), C channels visible to the loads
+static int make_im2col_map(CUtensorMap *map, const float *x, long long xs, int B, int H, int W, int C, int KH, int KW, int pad,
+                           int dil) {
+    EncodeIm2colFn fn = encode_im2col_fn();
+    if (!fn) return BTS_EINVAL;
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)xs * 4, (cuuint64_t)xs * 4 * W, (cuuint64_t)xs * 4 * W * H};
+    const int lower[2] = {-pad, -pad};                                        // bounding box lower corner (W, H)
+    const int upper[2] = {pad - dil * (KW - 1), pad - dil * (KH - 1)};        // upper corner: last base pixel = last output pixel
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), gdim, gstr, lower, upper,
+                          /*channelsPerPixel=*/32, /*pixelsPerColumn=*/BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
+
+// 0: activation tiles loaded by the producer warps (LDG); 1: staged by TMA where eligible; 2: bring-up variant of 1
+extern "C" int bts_conv_set_tma(int mode) {
+    if (mode < 0 || mode > 3) return BTS_EINVAL;
+    g_tma_mode = mode;
+    return 0;
+}
+extern "C" int bts_conv_get_tma(void) { return g_tma_mode; }
+
 struct BnBwdArgs {
     const float *x; long long xs; const float *st; int relu;
 };
@@ -800,22 +955,41 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
     const bool vec = p.vec_ok;      // aligned base + pixel stride % 4 == 0 (a channel tail is masked in-kernel)
     cudaError_t err = cudaSuccess;
-#define BTS_LAUNCH(PRE, UP, VEC)                                                                                   \
+    // ---- TMA-staged activation tiles (see the kernel's TMA template parameter): stride-1, non-up-sampled layers whose K
+    //      channels are a multiple of 32 (dense-quad K order == per-tap 32-channel chunks) and whose rows are 16-byte aligned
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool use_tma = false;
+    p.tma_adj = 0;
+    p.fd_kc = make_fastdiv((uint32_t)p.KC);
+    if (g_tma_mode != 0 && p.up == 0 && stride == 1 && p.vec_ok && (p.Cin % 32) == 0 && pad <= 127 &&
+        dil * (KH - 1) - pad <= 128 && dil * (KW - 1) - pad <= 128 && dil * (KH - 1) <= 255 && dil * (KW - 1) <= 255) {
+        const int rc = make_im2col_map(&tmap, x, x_pixel_stride, B, Hs, Ws, kwin ? Cin : p.Cin, KH, KW, pad, dil);
+        if (rc == 0) {
+            use_tma = true;
+            p.tma_adj = g_tma_mode == 2 ? 0 : pad;      // mode 2: alternative coordinate convention (bring-up switch)
+        } else if (g_tma_mode == 3) {
+            return rc;                                   // forced: report why the map could not be built
+        }
+    }
+#define BTS_LAUNCH(PRE, UP, VEC, TMA)                                                                              \
     do {                                                                                                           \
-        static bool attr_set_[BTS_MAX_DEVICES] = {}; bool &attr_set = attr_set_[bts_cur_device()];                                                                            \
+        static bool attr_set_[BTS_MAX_DEVICES] = {};                                                               \
+        bool &attr_set = attr_set_[bts_cur_device()];                                                              \
         if (!attr_set) {                                                                                           \
-            err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+            err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        SMEM_LIMIT);                                                                \
             if (err != cudaSuccess) return (int)err;                                                               \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        conv_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);                        \
+        conv_tc_kernel<PRE, UP, VEC, TMA><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p, tmap);             \
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                  \
     do {                                                      \
-        if (p.up == 2) { if (vec) BTS_LAUNCH(PRE, 2, true); else BTS_LAUNCH(PRE, 2, false); }    \
-        else if (p.up) { if (vec) BTS_LAUNCH(PRE, 1, true); else BTS_LAUNCH(PRE, 1, false); }    \
-        else { if (vec) BTS_LAUNCH(PRE, 0, true); else BTS_LAUNCH(PRE, 0, false); }              \
+        if (use_tma) BTS_LAUNCH(PRE, 0, true, true);                                                            \
+        else if (p.up == 2) { if (vec) BTS_LAUNCH(PRE, 2, true, false); else BTS_LAUNCH(PRE, 2, false, false); }    \
+        else if (p.up) { if (vec) BTS_LAUNCH(PRE, 1, true, false); else BTS_LAUNCH(PRE, 1, false, false); }    \
+        else { if (vec) BTS_LAUNCH(PRE, 0, true, false); else BTS_LAUNCH(PRE, 0, false, false); }              \
     } while (0)
     switch (pre) {
         case 0: BTS_DISPATCH_UV(0); break;

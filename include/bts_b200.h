@@ -130,6 +130,14 @@ int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, int Hs, int
                     int kwin, int Cin, int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                     const float *pre_scale, const float *pre_shift, int pre_relu, float *out, long long out_pixel_stride,
                     int act, int precision, double *stat_sum, double *stat_sumsq, void *stream);
+/* Staging of the activation tiles of bts_conv_fwd*: 0 = the producer warps load them (LDG + hi/lo split in registers),
+ * 1 = TMA im2col loads (cp.async.bulk.tensor -> UTMALDG.4D.IM2COL; zero padding by out-of-bounds fill) land the raw tile in
+ * shared memory as the A_hi operand and the producers only derive A_lo in place -- used for stride-1, non-up-sampled layers
+ * whose K channels are a multiple of 32 and whose rows are 16-byte aligned, every other layer keeps mode 0 automatically.
+ * (2, 3: bring-up variants.)  Process-wide setting. */
+int bts_conv_set_tma(int mode);
+int bts_conv_get_tma(void);
+
 /* dgrad (or any act-free conv) whose epilogue also reduces the BatchNorm(+ReLU)-backward sums of the layer in front of the
  * conv: the tile written is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat (zero them first),
  * mask = [bn(x)>0] when relu else 1, xhat = (x-mean)*invstd; bn_st = [4][Cout] scale|shift|mean|invstd.  Replaces the
