@@ -440,6 +440,134 @@ def run_lpg_config(args):
     return res
 
 
+# ------------------------------------------------------------------------------------------------ engine self-check
+# Round-2 fast paths (lean MMA issue loops, BatchNorm-backward sums in the dgrad epilogue, fused AdamW, CUDA-graph capture)
+# each have a switch.  Before timing, a SUBPROCESS checks each against an independent computation on the GPU at hand and the
+# bench only enables what passed -- a kernel bug then costs speed and is reported in the JSON line ("selfcheck"), it does not
+# silently produce a wrong number or kill the run (a device-side trap in the child leaves this process's context intact).
+SELFCHECK_FEATURES = ["lean_issue", "epi_bnbwd", "fused_adamw"]
+
+
+def selfcheck_child(enabled):
+    """runs in the child: prints 'CHECK <feature> <ok|fail> <detail>' lines; a crash after 'BEGIN <feature>' = that feature"""
+    import torch
+    import torch.nn.functional as F
+    from bts_b200 import _lib, conv, fused
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+
+    def relerr(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    def engine_ok():
+        worst = 0.0
+        for (B, Cin, H, W, Cout, k, pad, dil) in [(2, 192, 12, 20, 48, 3, 1, 1), (1, 240, 16, 24, 192, 1, 0, 1),
+                                                    (1, 128, 10, 12, 256, 3, 3, 3), (2, 36, 24, 32, 32, 3, 1, 1)]:
+            x = torch.randn(B, Cin, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev).requires_grad_(True)
+            y = conv.conv2d(x, w, 1, pad, dil)
+            gy = torch.randn(y.shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+            y.backward(gy)
+            xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+            yr = F.conv2d(xr, wr, None, 1, pad, dil)
+            yr.backward(gy)
+            torch.cuda.synchronize()
+            worst = max(worst, relerr(y.detach(), yr.detach()), relerr(x.grad, xr.grad), relerr(w.grad, wr.grad))
+        return worst < 2e-4, "worst rel-to-scale error %.2e vs torch fp32 conv (fwd/dgrad/wgrad, 4 layer shapes)" % worst
+
+    print("BEGIN lean_issue", flush=True)
+    L.bts_conv_set_issue_mode(1 if "lean_issue" in enabled else 0)
+    ok, det = engine_ok()
+    if "lean_issue" not in enabled:
+        print("CHECK lean_issue fail disabled after a crash; legacy loops: %s %s" % ("ok" if ok else "FAIL", det), flush=True)
+    elif not ok:
+        L.bts_conv_set_issue_mode(0)
+        ok2, det2 = engine_ok()
+        print("CHECK lean_issue fail %s; legacy loops: %s %s" % (det, "ok" if ok2 else "FAIL", det2), flush=True)
+    else:
+        print("CHECK lean_issue ok %s" % det, flush=True)
+
+    print("BEGIN epi_bnbwd", flush=True)
+    import torchvision
+    blk = torchvision.models.densenet._DenseBlock(3, 64, 4, 32, 0.0).to(dev).train()
+    from bts_b200 import model as M
+    M.adopt_convs(torch.nn.Sequential(blk))
+    xin = torch.randn(2, 64, 12, 16, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    grads = []
+    for flag in (False, True):
+        fused.EPI_BNBWD = flag
+        for q in blk.parameters():
+            q.grad = None
+        xi = xin.clone().requires_grad_(True)
+        out = blk(xi)
+        out.square().mean().backward()
+        torch.cuda.synchronize()
+        grads.append([xi.grad.clone()] + [q.grad.clone() for q in blk.parameters()])
+    worst = max(relerr(a, b) for a, b in zip(grads[1], grads[0]))
+    print("CHECK epi_bnbwd %s worst rel error %.2e vs the separate reduce pass (dense block, all gradients)"
+          % ("ok" if worst < 1e-4 else "fail", worst), flush=True)
+
+    print("BEGIN fused_adamw", flush=True)
+    from bts_b200.optim import FusedAdamW
+    pa = [torch.nn.Parameter(torch.randn(*sh, generator=g).to(dev)) for sh in [(48, 192, 3, 3), (7,), (513,), (64, 36, 3, 3)]]
+    pb = [torch.nn.Parameter(q.detach().clone()) for q in pa]
+    oa = torch.optim.AdamW([{"params": pa[:2], "weight_decay": 1e-2}, {"params": pa[2:], "weight_decay": 0}], lr=1e-4, eps=1e-3)
+    ob = FusedAdamW([{"params": pb[:2], "weight_decay": 1e-2}, {"params": pb[2:], "weight_decay": 0}], lr=1e-4, eps=1e-3, repack=False)
+    for _ in range(3):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(dev)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    ok = all(torch.allclose(a, b, rtol=1e-6, atol=1e-9) for a, b in zip(pa, pb))
+    print("CHECK fused_adamw %s vs torch.optim.AdamW after 3 steps" % ("ok" if ok else "fail"), flush=True)
+
+
+def _child_env():
+    """the child sees exactly this rank's GPU as cuda:0"""
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    ids = [v for v in vis.split(",") if v] if vis else None
+    dev = ids[local] if ids and local < len(ids) else str(local)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=dev)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    return env
+
+
+def run_selfcheck():
+    """parent side: returns {feature: (bool ok, detail)}; at most len(features)+1 child runs"""
+    enabled = list(SELFCHECK_FEATURES)
+    results = {}
+    for _attempt in range(len(SELFCHECK_FEATURES) + 1):
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--selfcheck-child", ",".join(enabled) or "none"],
+                                 capture_output=True, text=True, timeout=600, cwd=ROOT, env=_child_env())
+            text = out.stdout
+        except subprocess.TimeoutExpired as e:
+            text = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        begun, crashed = None, None
+        for line in text.splitlines():
+            f = line.split(None, 3)
+            if len(f) >= 2 and f[0] == "BEGIN":
+                begun = f[1]
+            elif len(f) >= 3 and f[0] == "CHECK":
+                results[f[1]] = (f[2] == "ok", f[3] if len(f) > 3 else "")
+                begun = None
+        if begun is not None:                      # the child died inside this feature's check
+            crashed = begun
+            results[crashed] = (False, "child process crashed during the check")
+        if crashed is None or crashed not in enabled:
+            break
+        enabled.remove(crashed)
+    for f in SELFCHECK_FEATURES:
+        results.setdefault(f, (False, "not reached"))
+    return results
+
+
 class StdoutToStderr:
     """While active, file descriptor 1 points at stderr: library chatter (e.g. the "NCCL version ..." banner NCCL prints on
     stdout at communicator creation) cannot precede the ONE JSON line this script owes its caller on stdout."""
@@ -522,8 +650,24 @@ def _run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     import bts
-    from bts_b200 import _lib, conv
+    from bts_b200 import _lib, conv, fused
     _lib.lib()                                   # fail loudly if the CUDA library is missing
+    selfcheck = None
+    if not args.no_selfcheck:
+        if rank == 0:
+            selfcheck = run_selfcheck()
+            flags = [1 if selfcheck[f][0] else 0 for f in SELFCHECK_FEATURES]
+        else:
+            flags = [1] * len(SELFCHECK_FEATURES)
+        if world > 1:
+            ft = torch.tensor(flags, device=dev, dtype=torch.int32)
+            dist.broadcast(ft, 0)
+            flags = [int(v) for v in ft.tolist()]
+        lean_ok, bnb_ok, adam_ok = [bool(v) for v in flags]
+        _lib.lib().bts_conv_set_issue_mode(1 if lean_ok else 0)
+        fused.EPI_BNBWD = bnb_ok
+        if not adam_ok:
+            args.optimizer = "torch"
     torch.backends.cudnn.benchmark = True        # bts_main.py:402
     torch.manual_seed(0)
     p = types.SimpleNamespace(encoder=cfg["encoder"], max_depth=cfg["max_depth"], dataset=cfg["dataset"], bts_size=512,
@@ -666,6 +810,8 @@ def _run_ours(args):
                     "n": K, "note": "rank-0 per-step CUDA-event durations inside the timed region"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if selfcheck is not None:
+        res["selfcheck"] = {f: {"enabled": bool(selfcheck[f][0]), "detail": selfcheck[f][1]} for f in SELFCHECK_FEATURES}
     if rank == 0:
         res["roofline_step"] = {"bound": "tensor", "achieved": res["value"] / world * cfg["gflop"] / 1e3,
                                 "unit": "TFLOP/s per GPU (nominal conv FLOPs %.1f GFLOP/img)" % cfg["gflop"]}
@@ -746,11 +892,16 @@ def main():
                     help="fused = bts_b200.optim.FusedAdamW (default), torch = torch.optim.AdamW exactly as bts_main.py")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="capture fwd+loss+bwd of the train step in one CUDA graph (auto: fall back to eager if capture fails)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the pre-flight parity check of the round-2 fast paths")
+    ap.add_argument("--selfcheck-child", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-lpg", action="store_true", help="skip the LPG roofline microbench")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager/cuDNN reference leg")
     ap.add_argument("--no-roofline", action="store_true", help="skip every evidence leg (peaks, traced step, LPG, baselines)")
     args = ap.parse_args()
+    if args.selfcheck_child is not None:
+        selfcheck_child(set(args.selfcheck_child.split(",")))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -85,6 +85,7 @@ SIGNATURES = {
     "bts_bn_bwd_coef": [_p, _p, _ll, _i, _p, _p, _p, _p, _p],
     "bts_conv_set_tma": [_i],
     "bts_conv_get_tma": [],
+    "bts_conv_set_issue_mode": [_i],
     "bts_conv_group_window": [_i, _i],
     "bts_conv_packed_floats_grouped": [_i, _i, _i, _i],
     "bts_conv_pack_weights_grouped": [_p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _p],

@@ -84,6 +84,7 @@ struct ConvParams {
     double *stat_sum, *stat_sumsq;   // optional per-output-channel sum / sum of squares of the (activated) output
     // BatchNorm-backward reduction fused into a dgrad's epilogue (bnb_x != null): the tile being written is g = dL/d relu(bn(x));
     // stat_sum[c] += sum_p g*[bn(x)>0],  stat_sumsq[c] += sum_p g*[bn(x)>0]*xhat   (bts_bn_relu_bwd_reduce without its pass)
+    int legacy;              // 1: round-1 single-lane MMA issue loop with separate A/B full barriers (fallback switch)
     int tma_adj;             // TMA mode: base-pixel coordinate = out*stride - tma_adj (the bounding box's lower corner)
     tc::FastDiv fd_kc;       // TMA mode: k-block -> (tap, 32-channel chunk) = (kb / KC, kb % KC)
     const float *bnb_x; long long bnb_xs;
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
     // ONE barrier per stage for the MMA warp (one try_wait per k-block).  TMA mode adds `raw` barriers for the loads:
     // TMA bytes (A raw tile + weights) land on raw(s), the lo-producers wait there and then arrive on full(s).
     auto raw = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-    auto full_b = [&](int s) { return TMA ? raw(s) : full_a(s); };
+    const bool legacy = p.legacy != 0;
+    auto full_b = [&](int s) { return (TMA || legacy) ? raw(s) : full_a(s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
     auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_a(s), TMA ? PRODUCER_THREADS : PRODUCER_THREADS + 1);
+            mbar_init(full_a(s), (TMA || legacy) ? PRODUCER_THREADS : PRODUCER_THREADS + 1);
             mbar_init(raw(s), 1);
             mbar_init(empty(s), 1);
         }
@@ -325,6 +327,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         //   * the precision / stacking mode is resolved outside the tile loop.
         // MMA count economy of round 1 is kept: n_tile <= 128 -> A_hi*[B_hi;B_lo] is ONE instruction of width 2*n_tile
         // (+ A_lo*B_hi): 2 MMAs per k-step; wider tiles: 3 MMAs per k-step over one 256-wide tile.
+        if (legacy) {
+            // ---- round-1 issue loop, kept verbatim as a fallback (bts_conv_set_issue_mode(0)): single lane, two barriers
+        if (lane == 0 && !TMA) {
+            // Instruction-count economy (measured, round 1): a tcgen05.mma with M=128, K=8 (tf32) costs ~115-130 cycles
+            // whatever N is -- fetching the 128 A rows from shared memory sets the pace -- so every layer ran at ~1400
+            // cycles per k-block (12 MMAs) regardless of Cout, load latency or producer instruction count.  Hence:
+            //   * n_tile <= 128: B_hi and B_lo are adjacent in the stage, so ONE instruction with N = 2*n_tile computes
+            //     A_hi*[B_hi;B_lo] into 2*n_tile accumulator columns (the epilogue adds the two halves); the third
+            //     product A_lo*B_hi is a second instruction: 2 MMAs per k-step instead of 3;
+            //   * n_tile <= 256 is one tile (3 MMAs per k-step, the activation tile produced once) instead of two tiles.
+            const bool stack = n_tile <= 128;
+            const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
+            const uint32_t idesc2 = make_idesc(BLOCK_M, 2 * n_tile);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int acc = ti & 1;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                mbar_wait(tmem_empty(acc), (uint32_t)((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+                    const uint32_t b_lo = b_hi + n_tile * 128;
+                    const uint64_t dah = make_desc(a_hi), dal = make_desc(a_lo), dbh = make_desc(b_hi), dbl = make_desc(b_lo);
+                    if (p.precision == 0) {
+                        if (stack) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 8; ++k) {
+                                umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc2, (kb | k) != 0);   // A_hi * [B_hi ; B_lo]
+                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, 1);                // A_lo * B_hi
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 8; ++k)   // small cross terms first
+                                umma_tf32(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 8; ++k) umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 8; ++k)
+                            umma_tf32(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(empty(s));       // frees the stage when these MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tmem_full(acc));     // accumulator of this tile complete
+            }
+        }
+        } else {
         const bool stack = n_tile <= 128;
         const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
         const uint32_t idesc2 = make_idesc(BLOCK_M, 2 * n_tile);
@@ -377,6 +436,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 if (++s == S) { s = 0; ph ^= 1; d = dA0; bfull = full_a(0); bempty = empty(0); }
             }
         }
+        }   // lean issue loop
     } else if (warp < 10) {
         // ===================== activation producers (2 groups x 4 warps) =====================
         const int pt = threadIdx.x - 64;           // 0..255
@@ -838,6 +898,8 @@ extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, lon
 
 // ---- TMA tensor map of the NHWC activation tensor, im2col mode (cuTensorMapEncodeIm2col through the runtime's driver
 //      entry-point query: no link-time dependency on libcuda)
+static int g_issue_legacy = 0;  // 1: round-1 MMA issue loops in conv_tc / wgrad_tc / wgrad2_tc (fallback switch)
+int bts_issue_legacy() { return g_issue_legacy; }
 static int g_tma_mode = 0;      // 0 off, 1 on, 2 on with base-pixel coordinates NOT shifted by the lower corner, 3 on + strict
 
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -881,6 +943,12 @@ extern "C" int bts_conv_set_tma(int mode) {
     return 0;
 }
 extern "C" int bts_conv_get_tma(void) { return g_tma_mode; }
+
+// 1 (default): lean whole-warp MMA issue loops; 0: the round-1 single-lane loops (kept as a fallback switch for bring-up)
+extern "C" int bts_conv_set_issue_mode(int lean) {
+    g_issue_legacy = lean ? 0 : 1;
+    return 0;
+}
 
 struct BnBwdArgs {
     const float *x; long long xs; const float *st; int relu;
@@ -961,8 +1029,9 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     memset(&tmap, 0, sizeof(tmap));
     bool use_tma = false;
     p.tma_adj = 0;
+    p.legacy = g_issue_legacy;
     p.fd_kc = make_fastdiv((uint32_t)p.KC);
-    if (g_tma_mode != 0 && p.up == 0 && stride == 1 && p.vec_ok && (p.Cin % 32) == 0 && pad <= 127 &&
+    if (g_tma_mode != 0 && !g_issue_legacy && p.up == 0 && stride == 1 && p.vec_ok && (p.Cin % 32) == 0 && pad <= 127 &&
         dil * (KH - 1) - pad <= 128 && dil * (KW - 1) - pad <= 128 && dil * (KH - 1) <= 255 && dil * (KW - 1) <= 255) {
         const int rc = make_im2col_map(&tmap, x, x_pixel_stride, B, Hs, Ws, kwin ? Cin : p.Cin, KH, KW, pad, dil);
         if (rc == 0) {

@@ -38,6 +38,7 @@ struct W2Params {
     int splitK, kb_per_split, KBq;
     int Mq;                  // B*Hin*Win input pixels
     int stages, stage_bytes, precision;
+    int legacy;              // 1: round-1 single-lane MMA issue loop (fallback switch)
 };
 
 template <int PRE, bool UP, bool VEC>
@@ -100,6 +101,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         // MMA issuer: whole warp in the loop, one elected lane issues (see conv_tc.cu: the round-1 single-lane loops paid
         // ~4 cycles x hundreds of issue-warp instructions per k-block).  With the taps packed along N the three products
         // of a k-group are 3 x ceil(taps*ncol/256) instructions instead of 3 x taps.
+        if (p.legacy) {
+        if (lane == 0) {
+            // A tcgen05.mma with M=128, K=8 costs ~115-130 cycles whatever N is (round-1 measurement: 54 per-tap MMAs
+            // per 16-pixel k-block = 5.5k cycles, exactly the observed k-block time).  With the taps packed along N the
+            // three products of a k-group are 3 x ceil(taps*ncol/256) instructions instead of 3 x taps.
+            const int n0 = n_total < 256 ? n_total : 256, n1 = n_total - n0;        // multiples of 16
+            const uint32_t idesc0 = make_idesc(BLOCK_CI, n0, 1, 1);
+            const uint32_t idesc1 = make_idesc(BLOCK_CI, n1 > 0 ? n1 : 16, 1, 1);
+            const uint64_t dah0 = make_desc_mn(base, CHUNK), dal0 = make_desc_mn(base + A_BYTES, CHUNK);
+            const uint64_t dbh0 = make_desc_mn(base + 2 * A_BYTES, CHUNK), dbl0 = make_desc_mn(base + 2 * A_BYTES + b_half, CHUNK);
+            const uint64_t piece1 = (uint64_t)((8 * CHUNK) >> 4), stage_step = (uint64_t)(p.stage_bytes >> 4);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint64_t so = (uint64_t)s * stage_step;
+#pragma unroll
+                for (int kg = 0; kg < KP / 8; ++kg) {
+                    const uint64_t o = so + (uint64_t)(kg * (1024 >> 4));   // start-address field: + 1024 B per k-group
+                    const uint32_t accumulate = (it | kg) != 0;
+                    if (p.precision == 0) {
+                        umma_tf32(tmem_base, dal0 + o, dbh0 + o, idesc0, accumulate);
+                        umma_tf32(tmem_base, dah0 + o, dbl0 + o, idesc0, 1);
+                        umma_tf32(tmem_base, dah0 + o, dbh0 + o, idesc0, 1);
+                        if (n1 > 0) {
+                            umma_tf32(tmem_base + 256, dal0 + o, dbh0 + o + piece1, idesc1, accumulate);
+                            umma_tf32(tmem_base + 256, dah0 + o, dbl0 + o + piece1, idesc1, 1);
+                            umma_tf32(tmem_base + 256, dah0 + o, dbh0 + o + piece1, idesc1, 1);
+                        }
+                    } else {
+                        umma_tf32(tmem_base, dah0 + o, dbh0 + o, idesc0, accumulate);
+                        if (n1 > 0) umma_tf32(tmem_base + 256, dah0 + o, dbh0 + o + piece1, idesc1, accumulate);
+                    }
+                }
+                umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            umma_commit(accum_full);
+        }
+        } else {
         const int n0 = n_total < 256 ? n_total : 256, n1 = n_total - n0;        // multiples of 16
         const uint32_t idesc0 = make_idesc(BLOCK_CI, n0, 1, 1);
         const uint32_t idesc1 = make_idesc(BLOCK_CI, n1 > 0 ? n1 : 16, 1, 1);
@@ -142,6 +184,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             if (++s == S) { s = 0; ph ^= 1; so = 0; bfull = full(0); bempty = empty(0); }
         }
         if (nkb == 0 && leader) umma_commit(accum_full);
+        }   // lean issue loop
     } else if (warp >= 2) {
         // 16 producer warps (round 1 ran 8: ncu showed ~9 cycles between a warp's instructions and 2.5 warps per
         // scheduler -- the per-thread instruction stream, not the tensor pipe, set the k-block time).  Quarter q of the
@@ -365,6 +408,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
 
 }  // namespace
 
+int bts_issue_legacy();
+
 // co-group width for the shifted-dY kernel: multiple of 16, taps*cg <= 512 TMEM columns, groups as even as possible
 int bts_wgrad2_cg(int Cout, int taps) {
     int cap = (512 / taps) / 16 * 16;
@@ -430,6 +475,7 @@ int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int u
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return BTS_EINVAL;
     p.precision = precision;
+    p.legacy = bts_issue_legacy();
     const int smem = p.stages * p.stage_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
     dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.cg - 1) / p.cg, splitK);
     const int pre = (pre_scale ? 2 : 0) | (pre_relu ? 1 : 0);

@@ -37,6 +37,7 @@ struct WgradParams {
     const float *dy; long long dys;
     int Cout, Hout, Wout;
     int n_tile;
+    int legacy;              // 1: round-1 single-lane MMA issue loop (fallback switch, bts_conv_set_issue_mode(0))
     int kwin;                // grouped (block-diagonal) layer: only the tiles ci_tile == nt exist, n_tile == kwin == 128
     float *part;             // [splitK][taps][Cin][Cout]   (grouped: [splitK][taps][Cin][kwin])
     int splitK, kb_per_split, KBp;
@@ -109,6 +110,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
         // 2 MMAs per k-group instead of 3: the dY_lo chunks follow the dY_hi chunks in the stage, so one instruction with
         // N = 32*nchunk + n_tile computes x_hi^T * [dY_hi ; dY_lo]; the epilogue adds the column blocks [0,n_tile) and
         // [32*nchunk, 32*nchunk+n_tile).  Wider tiles (n_tile > 128): three plain products per k-group.
+        if (p.legacy) {
+        if (lane == 0) {
+            // 2 MMAs per k-group instead of 3 (a tcgen05.mma with M=128, K=8 costs ~120 cycles whatever N is): the dY_lo
+            // chunks follow the dY_hi chunks in the stage, so one instruction with N = 32*nchunk + n_tile computes
+            // x_hi^T * [dY_hi ; dY_lo]; the epilogue adds the column blocks [0,n_tile) and [32*nchunk, 32*nchunk+n_tile).
+            const int nchunk_b = (n_tile + 31) >> 5;
+            const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
+            const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
+            const bool stack = n_tile <= 128;          // wider tiles: three plain products per k-group
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + (uint32_t)nchunk_b * CHUNK_BYTES;
+#pragma unroll
+                for (int kg = 0; kg < BLOCK_KP / 8; ++kg) {
+                    const uint64_t dah = make_desc_mn(a_hi + kg * 1024, CHUNK_BYTES), dal = make_desc_mn(a_lo + kg * 1024, CHUNK_BYTES);
+                    const uint64_t dbh = make_desc_mn(b_hi + kg * 1024, CHUNK_BYTES), dbl = make_desc_mn(b_lo + kg * 1024, CHUNK_BYTES);
+                    if (p.precision == 0 && stack) {
+                        umma_tf32(tmem_base, dah, dbh, idesc2, (it | kg) != 0);   // x_hi * [dY_hi ; dY_lo]
+                        umma_tf32(tmem_base, dal, dbh, idesc, 1);                 // x_lo * dY_hi
+                    } else if (p.precision == 0) {
+                        umma_tf32(tmem_base, dal, dbh, idesc, (it | kg) != 0);
+                        umma_tf32(tmem_base, dah, dbl, idesc, 1);
+                        umma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    } else {
+                        umma_tf32(tmem_base, dah, dbh, idesc, (it | kg) != 0);
+                    }
+                }
+                umma_commit(empty(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            umma_commit(accum_full);
+        }
+        } else {
         const int nchunk_b = (n_tile + 31) >> 5;
         const uint32_t idesc = make_idesc(BLOCK_CI, n_tile, 1, 1);
         const uint32_t idesc2 = make_idesc(BLOCK_CI, nchunk_b * 32 + n_tile, 1, 1);
@@ -159,6 +197,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
             if (++s == S) { s = 0; ph ^= 1; d = dA0; bfull = full(0); bempty = empty(0); }
         }
         if (nkb == 0 && leader) umma_commit(accum_full);      // empty split: release the epilogue (it writes zeros)
+        }   // lean issue loop
     } else if (warp >= 2) {
         // 8 warps per group (round 1 ran 4 with two pixel rows per thread: ~9 cycles between a warp's instructions at
         // 2.5 warps per scheduler made the producers, not the tensor pipe, set the k-block time): one pixel row of the
@@ -476,6 +515,8 @@ static int wgrad_n_tile(int Cout) {
     return n;
 }
 
+int bts_issue_legacy();      // conv_tc.cu: 1 = round-1 MMA issue loops (fallback switch)
+
 // narrow-output 3x3 layers use the shifted-dY kernel (wgrad2_tc.cu)
 bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq);
 void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK);
@@ -541,6 +582,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
     p.M = (int)M;
     p.n_tile = wgrad_n_tile(Cout);
     p.kwin = 0;
+    p.legacy = bts_issue_legacy();
     p.part = workspace; p.splitK = splitK;
     p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
     p.kb_per_split = (p.KBp + splitK - 1) / splitK;
@@ -615,6 +657,7 @@ extern "C" int bts_conv_wgrad(const float *x, long long x_pixel_stride, int B, i
 // (width, cpg, KH, KW).  Only the diagonal 128 x 128 channel blocks are computed (one CTA per block, tap and split),
 // the reduce kernel extracts every group's cpg x cpg sub-block.  Requires bts_conv_group_window(width, cpg) == 128.
 extern "C" int bts_conv_group_window(int width, int cpg);
+int bts_issue_legacy();
 
 static long long wgrad_grouped_split(long long M, int width, int taps) {
     const long long KBp = (M + BLOCK_KP - 1) / BLOCK_KP;
@@ -665,6 +708,7 @@ extern "C" int bts_conv_wgrad_grouped(const float *x, long long x_pixel_stride, 
     if ((long long)B * Hs * Ws * x_pixel_stride >= 0x7fffffffLL || M * dy_pixel_stride >= 0x7fffffffLL) return BTS_EINVAL;
     p.M = (int)M;
     p.n_tile = 128; p.kwin = 128;
+    p.legacy = bts_issue_legacy();
     p.part = workspace; p.splitK = splitK;
     p.KBp = (int)((M + BLOCK_KP - 1) / BLOCK_KP);
     p.kb_per_split = (p.KBp + splitK - 1) / splitK;

@@ -137,6 +137,9 @@ int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, int Hs, int
  * (2, 3: bring-up variants.)  Process-wide setting. */
 int bts_conv_set_tma(int mode);
 int bts_conv_get_tma(void);
+/* MMA issue loops of the three tensor-core kernels: 1 (default) = whole-warp loop with one elected lane, one barrier per stage,
+ * incrementally advanced descriptors; 0 = the round-1 single-lane loops, kept as a bring-up fallback.  Process-wide. */
+int bts_conv_set_issue_mode(int lean);
 
 /* dgrad (or any act-free conv) whose epilogue also reduces the BatchNorm(+ReLU)-backward sums of the layer in front of the
  * conv: the tile written is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat (zero them first),
