@@ -665,7 +665,7 @@ def _run_ours(args):
             flags = [int(v) for v in ft.tolist()]
         lean_ok, bnb_ok, adam_ok = [bool(v) for v in flags]
         _lib.lib().bts_conv_set_issue_mode(1 if lean_ok else 0)
-        fused.EPI_BNBWD = bnb_ok
+        fused.EPI_BNBWD = fused.EPI_BNBWD and bnb_ok      # off by default (measured slower, bts_b200/fused.py); opt-in via env
         if not adam_ok:
             args.optimizer = "torch"
     torch.backends.cudnn.benchmark = True        # bts_main.py:402

@@ -51,6 +51,9 @@ def trace_report():
     return sorted(((t, n, k, f) for k, (t, n, f) in agg.items()), reverse=True)
 
 
+if _os.environ.get("BTS_B200_TMA") is not None:            # bring-up switch for the TMA-staged activation tiles
+    _lib.lib().bts_conv_set_tma(int(_os.environ["BTS_B200_TMA"]))
+
 _pack_cache = {}   # id(weight) -> (weakref, version, data_ptr, transpose) -> packed tensor
 
 

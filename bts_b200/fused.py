@@ -86,7 +86,11 @@ def bn_relu_backward(x, g, st, use_stats, out, accumulate):
     return S
 
 
-EPI_BNBWD = True    # BatchNorm-backward sums reduced in the dgrad epilogue (bts_conv_fwd_bnbwd) instead of a separate pass
+# BatchNorm-backward sums reduced in the dgrad epilogue (bts_conv_fwd_bnbwd) instead of a separate pass.  Measured on B200
+# (profiles/r02_*): the four epilogue warps already pace the short-K dgrads, and the extra strided reads of x + the
+# per-channel parameters doubled their time (dgrad 20.0 -> 33.4 ms per K16 step against 7.4 ms of reduce passes saved), so the
+# separate streaming reduce pass is the default; the fused form stays available (and tested) for long-K layers.
+EPI_BNBWD = os.environ.get("BTS_B200_EPI_BNBWD", "0") == "1"
 
 
 def bn_relu_backward_from_sums(x, g, st, S, use_stats, out, accumulate):

@@ -22,9 +22,20 @@ def _block(C0, L, growth=48, bn_size=4):
     return blk
 
 
+@pytest.fixture(params=[False, True], ids=["bn_reduce_pass", "bn_sums_in_dgrad_epilogue"])
+def epi_bnbwd(request):
+    """both forms of the BatchNorm backward: separate streaming reduce pass (default) and the sums reduced in the dgrad
+    epilogue (bts_conv_fwd_bnbwd)"""
+    from bts_b200 import fused
+    prev = fused.EPI_BNBWD
+    fused.EPI_BNBWD = request.param
+    yield request.param
+    fused.EPI_BNBWD = prev
+
+
 @pytest.mark.parametrize("mode", ["train", "eval"])
-@pytest.mark.parametrize("C0,L,H,W", [(96, 3, 12, 20), (64, 2, 9, 7)])
-def test_dense_block_matches_torchvision(mode, C0, L, H, W):
+@pytest.mark.parametrize("C0,L,H,W", [(96, 3, 12, 20), (64, 2, 9, 7), (208, 2, 6, 10)])
+def test_dense_block_matches_torchvision(epi_bnbwd, mode, C0, L, H, W):
     from bts_b200 import model as M
     ref = _block(C0, L).double()
     ours = copy.deepcopy(ref).float()

@@ -150,7 +150,7 @@ int main() {
                     at[0].val.clusterDim.y = 1;
                     at[0].val.clusterDim.z = 1;
                     cfg.attrs = at;
-                    cfg.numAttrs = 1;
+                    cfg.numAttrs = mode == 3 ? 1 : 0;      // plain launch unless the kernel runs as CTA pairs
                     cudaError_t e = cudaLaunchKernelEx(&cfg, mma_bench, mode, N, iters, bg, pattern, d_out);
                     if (e == cudaSuccess) e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) {
