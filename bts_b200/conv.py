@@ -29,7 +29,18 @@ def set_trace(on):
     del trace_log[:]
 
 
+SYNC_DEBUG = _os.environ.get("BTS_B200_SYNC", "0") == "1"    # bring-up: synchronize after every engine call, name the failing one
+
+
 def _traced(kind, desc, fn, flops=0.0):
+    if SYNC_DEBUG:
+        out = fn()
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            print("BTS_B200_SYNC: engine call failed: %s %s (%s)" % (kind, desc, str(e).splitlines()[0]), flush=True)
+            raise
+        return out
     if not TRACE:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

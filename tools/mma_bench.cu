@@ -51,7 +51,8 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 // mode 0: SS K-major   1: SS MN-major   2: TS (A in TMEM), B K-major   3: cta_group::2 SS K-major (M = 256 over the pair)
 // bg: number of background warps streaming st.shared.v4 into a separate 64 KB region while the MMAs run
 // distinct: 1 -> the 4 k-steps x `stages` stage slots are walked (distinct smem addresses), 0 -> one address re-read
-__global__ void __launch_bounds__(320, 1) mma_bench(int mode, int N, int iters, int bg, int pattern, long long *out) {
+template <int mode>
+__global__ void __launch_bounds__(320, 1) mma_bench(int N, int iters, int bg, int pattern, long long *out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -61,8 +62,9 @@ __global__ void __launch_bounds__(320, 1) mma_bench(int mode, int N, int iters, 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + bar_off + 16);
     volatile int *stop = reinterpret_cast<volatile int *>(sm + bar_off + 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool two = mode == 3;
-    const uint32_t rank = two ? cluster_rank() : 0;
+    constexpr bool two = mode == 3;
+    uint32_t rank = 0;
+    if constexpr (two) rank = cluster_rank();
     for (uint32_t i = threadIdx.x; i < 224 * 1024 / 16; i += blockDim.x) st_shared_v4(base + i * 16, 1.f, 0.5f, 0.25f, 2.f);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -70,12 +72,12 @@ __global__ void __launch_bounds__(320, 1) mma_bench(int mode, int N, int iters, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        if (two) tmem_alloc2(smem_u32(tmem_slot), 512);
+        if constexpr (two) tmem_alloc2(smem_u32(tmem_slot), 512);
         else tmem_alloc(smem_u32(tmem_slot), 512);
     }
     fence_proxy_async();
     tc_fence_before();
-    if (two) cluster_sync_all(); else __syncthreads();
+    if constexpr (two) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     long long t0 = 0, t1 = 0;
@@ -89,13 +91,13 @@ __global__ void __launch_bounds__(320, 1) mma_bench(int mode, int N, int iters, 
                 const uint32_t a = base + a_off + s * 16384, b = base + b_off + s * 32768;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (mode == 0) umma_tf32(tmem_base, make_desc(a) + 2 * k, make_desc(b) + 2 * k, idesc, 1);
-                    else if (mode == 1) umma_tf32(tmem_base, make_desc_mn(a + k * 1024, 4096), make_desc_mn(b + k * 1024, 4096), idesc, 1);
-                    else if (mode == 2) umma_tf32_ts(tmem_base, tmem_base + 256 + (s * 4 + k) * 8, make_desc(b) + 2 * k, idesc, 1);
+                    if constexpr (mode == 0) umma_tf32(tmem_base, make_desc(a) + 2 * k, make_desc(b) + 2 * k, idesc, 1);
+                    else if constexpr (mode == 1) umma_tf32(tmem_base, make_desc_mn(a + k * 1024, 4096), make_desc_mn(b + k * 1024, 4096), idesc, 1);
+                    else if constexpr (mode == 2) umma_tf32_ts(tmem_base, tmem_base + 256 + (s * 4 + k) * 8, make_desc(b) + 2 * k, idesc, 1);
                     else umma_tf32_2cta(tmem_base, make_desc(a) + 2 * k, make_desc(b) + 2 * k, idesc, 1);
                 }
             }
-            if (two) umma_commit_2cta(bar, 3); else umma_commit(bar);
+            if constexpr (two) umma_commit_2cta(bar, 3); else umma_commit(bar);
             mbar_wait(bar, 0);
             t1 = clock64();
             *stop = 1;
@@ -114,9 +116,9 @@ __global__ void __launch_bounds__(320, 1) mma_bench(int mode, int N, int iters, 
         }
     }
     tc_fence_before();
-    if (two) cluster_sync_all(); else __syncthreads();
+    if constexpr (two) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
-        if (two) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+        if constexpr (two) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
     if (threadIdx.x == 32 && rank == 0) out[blockIdx.x] = t1 - t0;
 }
@@ -130,7 +132,10 @@ int main() {
     long long *d_out;
     cudaMalloc(&d_out, sizeof(long long) * sms);
     const int smem = 226 * 1024;
-    cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(mma_bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(mma_bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(mma_bench<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(mma_bench<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int iters = 2048;
     printf("mode,N,bg_warps,pattern,cycles_per_mma_median,cycles_min,cycles_max\n");
     const int Ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
@@ -140,27 +145,36 @@ int main() {
                 for (int N : Ns) {
                     if (mode == 3 && N < 32) continue;
                     cudaMemset(d_out, 0, sizeof(long long) * sms);
-                    cudaLaunchConfig_t cfg{};
-                    cfg.gridDim = dim3(mode == 3 ? (sms / 2) * 2 : sms);
-                    cfg.blockDim = dim3(320);
-                    cfg.dynamicSmemBytes = smem;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = mode == 3 ? 2 : 1;
-                    at[0].val.clusterDim.y = 1;
-                    at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at;
-                    cfg.numAttrs = mode == 3 ? 1 : 0;      // plain launch unless the kernel runs as CTA pairs
-                    cudaError_t e = cudaLaunchKernelEx(&cfg, mma_bench, mode, N, iters, bg, pattern, d_out);
+                    cudaError_t e = cudaSuccess;
+                    const int grid = mode == 3 ? (sms / 2) * 2 : sms;
+                    if (mode == 0) mma_bench<0><<<grid, 320, smem>>>(N, iters, bg, pattern, d_out);
+                    else if (mode == 1) mma_bench<1><<<grid, 320, smem>>>(N, iters, bg, pattern, d_out);
+                    else if (mode == 2) mma_bench<2><<<grid, 320, smem>>>(N, iters, bg, pattern, d_out);
+                    else {
+                        cudaLaunchConfig_t cfg{};
+                        cfg.gridDim = dim3(grid);
+                        cfg.blockDim = dim3(320);
+                        cfg.dynamicSmemBytes = smem;
+                        cudaLaunchAttribute at[1];
+                        at[0].id = cudaLaunchAttributeClusterDimension;
+                        at[0].val.clusterDim.x = 2;
+                        at[0].val.clusterDim.y = 1;
+                        at[0].val.clusterDim.z = 1;
+                        cfg.attrs = at;
+                        cfg.numAttrs = 1;
+                        e = cudaLaunchKernelEx(&cfg, mma_bench<3>, N, iters, bg, pattern, d_out);
+                    }
+                    if (e == cudaSuccess) e = cudaGetLastError();
                     if (e == cudaSuccess) e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) {
                         printf("%d,%d,%d,%d,ERROR %s\n", mode, N, bg, pattern, cudaGetErrorString(e));
+                        if (mode == 3) break;          // keep the other modes' results
                         return 1;
                     }
                     std::vector<long long> h(sms);
                     cudaMemcpy(h.data(), d_out, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
                     std::vector<double> v;
-                    for (int i = 0; i < (int)cfg.gridDim.x; ++i)
+                    for (int i = 0; i < grid; ++i)
                         if (h[i] > 0) v.push_back((double)h[i] / (iters * 4.0));
                     std::sort(v.begin(), v.end());
                     printf("%d,%d,%d,%d,%.1f,%.1f,%.1f\n", mode, N, bg, pattern, v[v.size() / 2], v.front(), v.back());
