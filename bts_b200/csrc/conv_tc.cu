@@ -496,6 +496,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 }
                 const uint32_t a_hi = base + (uint32_t)s_t * stage_bytes + roff0;
                 const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                // First make sure the PREVIOUS use of this stage was consumed (what the loader waited for before re-arming
+                // raw): a parity wait only tells adjacent phases apart, and a group that runs ahead of the other group's
+                // k-block on the same stage would otherwise see the phase before last as "complete" and read a stale tile.
+                mbar_wait(empty(s_t), ph_t ^ 1);
                 mbar_wait(raw(s_t), ph_t);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
