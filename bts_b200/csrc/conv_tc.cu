@@ -84,8 +84,11 @@ struct ConvParams {
     double *stat_sum, *stat_sumsq;   // optional per-output-channel sum / sum of squares of the (activated) output
     // BatchNorm-backward reduction fused into a dgrad's epilogue (bnb_x != null): the tile being written is g = dL/d relu(bn(x));
     // stat_sum[c] += sum_p g*[bn(x)>0],  stat_sumsq[c] += sum_p g*[bn(x)>0]*xhat   (bts_bn_relu_bwd_reduce without its pass)
+    int chunk_major;         // K order: k-block kb = (chunk kb / taps, tap kb % taps) -- consecutive k-blocks re-read the SAME
+                             // pixels' lines shifted by one tap, so they hit in L1 instead of going to L2 nine times
     int legacy;              // 1: round-1 single-lane MMA issue loop with separate A/B full barriers (fallback switch)
     int tma_adj;             // TMA mode: base-pixel coordinate = out*stride - tma_adj (the bounding box's lower corner)
+    tc::FastDiv fd_taps;     // chunk-major: kb -> (kb / taps, kb % taps)
     tc::FastDiv fd_kc;       // TMA mode: k-block -> (tap, 32-channel chunk) = (kb / KC, kb % KC)
     const float *bnb_x; long long bnb_xs;
     const float *bnb_st;             // [4][Cout]: scale, shift, mean, invstd
@@ -107,7 +110,8 @@ using namespace tc;
 // transpose_flip=1 packs the dgrad operator: rows = ci, k = (flipped tap, co).
 __device__ __forceinline__ void pack_one(const float *__restrict__ w, long long s_co, long long s_ci, long long s_kh,
                                          long long s_kw, int Cout, int Cin, int KH, int KW, int transpose_flip,
-                                         float *__restrict__ wpack, int n_tile, int kwin, int cpg, long long idx) {
+                                         float *__restrict__ wpack, int n_tile, int kwin, int cpg, int flags,
+                                         long long idx) {
     // grouped (kwin > 0): Cin == Cout == total width, w is (width, cpg, KH, KW); rows = all channels, the K channels of
     // n-tile nt are the window [nt*kwin, (nt+1)*kwin) and entries outside the row's group are zero (block diagonal)
     const int Nrows = transpose_flip ? Cin : Cout;    // GEMM N
@@ -122,8 +126,13 @@ __device__ __forceinline__ void pack_one(const float *__restrict__ w, long long 
     const int kb = (int)(t % KB);
     const int nt = (int)(t / KB);
     const int g = kb * 8 + (kk >> 2);
-    const int tap = g / CQ;
-    const int row = nt * n_tile + n, ch = (g - tap * CQ) * 4 + (kk & 3);
+    int tap = g / CQ;
+    int ch = (g - tap * CQ) * 4 + (kk & 3);
+    if (flags & 1) {                      // chunk-major K order (Kch % 32 == 0): k-block = (32-channel chunk, tap), taps innermost
+        tap = kb % taps;
+        ch = (kb / taps) * 32 + kk;
+    }
+    const int row = nt * n_tile + n;
     float val = 0.f;
     if (row < Nrows && tap < taps && ch < Kch) {
         int kh = tap / KW, kw = tap % KW;
@@ -155,13 +164,13 @@ __device__ __forceinline__ void pack_one(const float *__restrict__ w, long long 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, long long s_co, long long s_ci,
                                                            long long s_kh, long long s_kw, int Cout, int Cin, int KH,
                                                            int KW, int transpose_flip, float *__restrict__ wpack,
-                                                           int n_tile, int n_tiles, int kwin, int cpg) {
+                                                           int n_tile, int n_tiles, int kwin, int cpg, int flags) {
     const int Kch = kwin ? kwin : (transpose_flip ? Cout : Cin);
     const int KB = (KH * KW * ((Kch + 3) / 4) + 7) / 8;
     const long long total = (long long)n_tiles * KB * n_tile * 32;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x)
-        pack_one(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW, transpose_flip, wpack, n_tile, kwin, cpg, idx);
+        pack_one(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW, transpose_flip, wpack, n_tile, kwin, cpg, flags, idx);
 }
 
 // every packed operator of a model in ONE launch (after an optimizer step: 394 launches -> 1 for DenseNet-161 + decoder)
@@ -170,7 +179,7 @@ struct PackDesc {
     float *wpack;
     long long s_co, s_ci, s_kh, s_kw;
     long long start;                     // first global index of this operator (prefix sum of packed_floats / 2)
-    int Cout, Cin, KH, KW, transpose_flip, n_tile, n_tiles, kwin, cpg, pad_;
+    int Cout, Cin, KH, KW, transpose_flip, n_tile, n_tiles, kwin, cpg, flags;   // flags bit 0: chunk-major K order
 };
 static_assert(sizeof(PackDesc) == 96, "PackDesc layout is mirrored by bts_b200/conv.py");
 
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc 
         }
         const PackDesc &q = d[lo];
         pack_one(q.w, q.s_co, q.s_ci, q.s_kh, q.s_kw, q.Cout, q.Cin, q.KH, q.KW, q.transpose_flip, q.wpack, q.n_tile, q.kwin,
-                 q.cpg, idx - q.start);
+                 q.cpg, q.flags, idx - q.start);
     }
 }
 
@@ -532,6 +541,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block this group loads; this lane's channel
         //      quad of that k-block is g = 8 kb + chunk -> (tap, quad in tap) by multiply-shift division
         int oy[8], ox[8], rowoff[8];
+        uint32_t tmask[8];                         // bit t: filter tap t of this row falls inside the image (taps <= 32, no up-sample)
+        const bool use_tm = (UP == 0) && taps <= 32;
         int l_ti = 0, l_kb = grp, cur_ti = -1;
         while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         auto set_tile = [&](int ti) {
@@ -560,8 +571,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ---- load phase: this lane's 8 x 16-byte global loads of one k-block (predicated, branch-free)
         auto load_kb = [&](F4(&v)[8], uint32_t &mask, int &c_out) {
             if (l_ti != cur_ti) set_tile(l_ti);
-            const uint32_t g = (uint32_t)(l_kb * 8 + chunk);
-            const uint32_t tap = fdiv(g, p.fd_cq);
+            uint32_t g = (uint32_t)(l_kb * 8 + chunk);
+            uint32_t tap = fdiv(g, p.fd_cq);
+            if (p.chunk_major) {                   // (chunk, tap) order: one tap per k-block, the chunk advances every `taps` k-blocks
+                const uint32_t kc = fdiv((uint32_t)l_kb, p.fd_taps);
+                tap = (uint32_t)l_kb - kc * (uint32_t)taps;
+                g = tap * (uint32_t)p.CQ + kc * 8u + (uint32_t)chunk;
+            }
             const uint32_t ky = fdiv(tap, p.fd_kw);
             const int kx = (int)(tap - ky * (uint32_t)KW);
             const int dy = (int)ky * dil, dx = kx * dil;
@@ -573,7 +589,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int yy = oy[i] + dy, xx = ox[i] + dx;
-                bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                bool ok;
+                if (use_tm) ok = cok && ((tmask[i] >> tap) & 1u);
+                else ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
                 if (UP == 2) ok = ok && (((yy | xx) & 1) == 0);          // zero-stuffed source: odd coordinates are zeros
                 mk |= (ok ? 1u : 0u) << i;
                 int off;
@@ -623,26 +641,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     for (int e = 1; e < 4; ++e)
                         if (c + e >= Cin) v[i].v[e] = 0.f;
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            // hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is exact in fp32
+            // and the tensor core reads its top 19 bits.  (Truncating instead of rounding saves one op per element but
+            // makes lo one-signed: the dropped lo*lo term and lo's own truncation then add up coherently over K -- measured
+            // 2-3x the error, past the 2e-5 bar of tests/test_conv_gpu.py -- so the rounding stays.)
+            auto split4 = [&](const float (&a)[4], uint32_t row_off) {
                 float hi[4], lo[4];
-                const bool live = (mask >> i) & 1u;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float a = v[i].v[e];
-                    if (AFF) {
-                        a = fmaf(a, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
-                        if (RELU) a = fmaxf(a, 0.f);
-                        a = live ? a : 0.f;                     // zero padding is applied after the pre-op
-                    } else if (RELU) {
-                        a = fmaxf(a, 0.f);                      // padded lanes were loaded as 0
-                    }
-                    const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
-                    hi[e] = h;
-                    lo[e] = a - h;
+                    hi[e] = __uint_as_float((__float_as_uint(a[e]) + 0x1000u) & 0xffffe000u);
+                    lo[e] = a[e] - hi[e];
                 }
-                st_shared_v4(a_hi + (uint32_t)i * 2048u, hi[0], hi[1], hi[2], hi[3]);
-                st_shared_v4(a_lo + (uint32_t)i * 2048u, lo[0], lo[1], lo[2], lo[3]);
+                st_shared_v4(a_hi + row_off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + row_off, lo[0], lo[1], lo[2], lo[3]);
+            };
+            if (AFF && mask == 0xffu) {
+                // interior rows (no tap in the padding): no per-element select
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] = fmaf(v[i].v[e], sc[e], sh[e]);
+                        if (RELU) a[e] = fmaxf(a[e], 0.f);
+                    }
+                    split4(a, (uint32_t)i * 2048u);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool live = (mask >> i) & 1u;
+                    float a[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = v[i].v[e];
+                        if (AFF) {
+                            t = fmaf(t, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
+                            if (RELU) t = fmaxf(t, 0.f);
+                            t = live ? t : 0.f;                     // zero padding is applied after the pre-op
+                        } else if (RELU) {
+                            t = fmaxf(t, 0.f);                      // padded lanes were loaded as 0
+                        }
+                        a[e] = t;
+                    }
+                    split4(a, (uint32_t)i * 2048u);
+                }
             }
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(bar_full);
@@ -844,8 +887,10 @@ extern "C" long long bts_conv_packed_floats(int n_rows, int k_channels, int KH, 
 }
 
 extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
-                                     int Cout, int Cin, int KH, int KW, int transpose_flip, float *wpack, void *stream) {
+                                     int Cout, int Cin, int KH, int KW, int transpose_flip, int flags, float *wpack,
+                                     void *stream) {
     if (!w || !wpack || Cout < 1 || Cin < 1 || KH < 1 || KW < 1) return BTS_EINVAL;
+    if ((flags & 1) && ((transpose_flip ? Cout : Cin) % 32)) return BTS_EINVAL;      // chunk-major needs whole 32-channel chunks
     if (!bts_aligned16(wpack)) return BTS_EALIGN;
     const int rows = transpose_flip ? Cin : Cout;
     const int n_tile = bts_conv_n_tile(rows);
@@ -855,7 +900,7 @@ extern "C" int bts_conv_pack_weights(const float *w, long long s_co, long long s
     const long long cap = (long long)bts_num_sms() * 16;
     if (grid > cap) grid = cap;
     pack_weights_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(w, s_co, s_ci, s_kh, s_kw, Cout, Cin, KH, KW,
-                                                                    transpose_flip, wpack, n_tile, n_tiles, 0, 1);
+                                                                    transpose_flip, wpack, n_tile, n_tiles, 0, 1, flags);
     BTS_LAUNCH_CHECK();
     return 0;
 }
@@ -884,8 +929,8 @@ extern "C" long long bts_conv_packed_floats_grouped(int width, int cpg, int KH, 
 }
 
 extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, long long s_ci, long long s_kh, long long s_kw,
-                                             int width, int cpg, int KH, int KW, int transpose_flip, float *wpack,
-                                             void *stream) {
+                                             int width, int cpg, int KH, int KW, int transpose_flip, int flags,
+                                             float *wpack, void *stream) {
     if (!w || !wpack || KH < 1 || KW < 1) return BTS_EINVAL;
     const int kwin = bts_conv_group_window(width, cpg);
     if (!kwin) return BTS_EINVAL;
@@ -895,7 +940,7 @@ extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, lon
     const long long cap = (long long)bts_num_sms() * 16;
     if (grid > cap) grid = cap;
     pack_weights_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(w, s_co, s_ci, s_kh, s_kw, width, width, KH, KW,
-                                                                    transpose_flip, wpack, kwin, width / kwin, kwin, cpg);
+                                                                    transpose_flip, wpack, kwin, width / kwin, kwin, cpg, flags);
     BTS_LAUNCH_CHECK();
     return 0;
 }
@@ -963,7 +1008,7 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
                          int KH, int KW, int stride, int pad, int dil, const float *wpack, int Cout,
                          const float *pre_scale, const float *pre_shift, int pre_relu, float *out,
                          long long out_pixel_stride, int act, int precision, double *stat_sum, double *stat_sumsq,
-                         void *stream, const BnBwdArgs *bnb = nullptr) {
+                         void *stream, const BnBwdArgs *bnb = nullptr, int flags = 0) {
     if (!x || !wpack || !out || B < 0 || Hs < 1 || Ws < 1 || Cin < 1 || Cout < 1 || KH < 1 || KW < 1 || stride < 1 ||
         pad < 0 || dil < 1)
         return BTS_EINVAL;
@@ -1022,6 +1067,10 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes - stat_bytes) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return BTS_EINVAL;
+    p.chunk_major = (flags & 1) ? 1 : 0;
+    if (p.chunk_major && ((p.Cin % 32) || p.up)) return BTS_EINVAL;
+    if (p.chunk_major && p.stages > 3) p.stages = 3;   // leave most of the SM's 228 KB to L1: consecutive k-blocks of a chunk
+                                                        // re-read the same pixels' lines shifted by one tap
     const int smem = p.stages * p.stage_bytes + pre_bytes + BAR_BYTES + stat_bytes + 1024;
     const int sms = bts_num_sms();
     dim3 grid((unsigned)(p.total_tiles < sms ? p.total_tiles : sms));
@@ -1034,8 +1083,9 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     bool use_tma = false;
     p.tma_adj = 0;
     p.legacy = g_issue_legacy;
+    p.fd_taps = make_fastdiv((uint32_t)(KH * KW));
     p.fd_kc = make_fastdiv((uint32_t)p.KC);
-    if (g_tma_mode != 0 && !g_issue_legacy && p.up == 0 && stride == 1 && p.vec_ok && (p.Cin % 32) == 0 && pad <= 127 &&
+    if (g_tma_mode != 0 && !g_issue_legacy && !p.chunk_major && p.up == 0 && stride == 1 && p.vec_ok && (p.Cin % 32) == 0 && pad <= 127 &&
         dil * (KH - 1) - pad <= 128 && dil * (KW - 1) - pad <= 128 && dil * (KH - 1) <= 255 && dil * (KW - 1) <= 255) {
         const int rc = make_im2col_map(&tmap, x, x_pixel_stride, B, Hs, Ws, kwin ? Cin : p.Cin, KH, KW, pad, dil);
         if (rc == 0) {
@@ -1106,10 +1156,10 @@ extern "C" int bts_conv_fwd_ex(const float *x, long long x_pixel_stride, int B, 
                                int out_w, int kwin, int Cin, int KH, int KW, int stride, int pad, int dil,
                                const float *wpack, int Cout, const float *pre_scale, const float *pre_shift, int pre_relu,
                                float *out, long long out_pixel_stride, int act, int precision, double *stat_sum,
-                               double *stat_sumsq, void *stream) {
+                               double *stat_sumsq, int flags, void *stream) {
     return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, source_mode, out_h, out_w, kwin, Cin, KH, KW, stride, pad, dil, wpack,
                          Cout, pre_scale, pre_shift, pre_relu, out, out_pixel_stride, act, precision, stat_sum, stat_sumsq,
-                         stream);
+                         stream, nullptr, flags);
 }
 
 // descs: device array of n PackDesc (layout above; built by the host side once per model), total = sum of packed_floats / 2
@@ -1132,8 +1182,8 @@ extern "C" int bts_conv_fwd_bnbwd(const float *x, long long x_pixel_stride, int 
                                   int out_w, int kwin, int Cin, int KH, int KW, int stride, int pad, int dil,
                                   const float *wpack, int Cout, float *out, long long out_pixel_stride, int precision,
                                   const float *x_bn, long long x_bn_stride, const float *bn_st, int relu, double *S1,
-                                  double *S2, void *stream) {
+                                  double *S2, int flags, void *stream) {
     BnBwdArgs a{x_bn, x_bn_stride, bn_st, relu};
     return conv_fwd_impl(x, x_pixel_stride, B, Hs, Ws, source_mode, out_h, out_w, kwin, Cin, KH, KW, stride, pad, dil, wpack,
-                         Cout, nullptr, nullptr, 0, out, out_pixel_stride, 0, precision, S1, S2, stream, &a);
+                         Cout, nullptr, nullptr, 0, out, out_pixel_stride, 0, precision, S1, S2, stream, &a, flags);
 }

@@ -356,22 +356,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             mbar_arrive(full(s));
         };
         {
-            // three register buffers: two k-blocks of loads in flight while one is split and stored (ncu, round 1: the producer
-            // warps sat in long-scoreboard stalls -- one look-ahead of a 16-pixel k-block does not cover the load latency)
-            F4 a0[NAU], a1[NAU], a2[NAU], b0[NBU], b1[NBU], b2[NBU];
-            bool k0 = false, k1 = false, k2 = false;
-            if (0 < nkb) load(0, a0, b0, k0);
-            if (1 < nkb) load(1, a1, b1, k1);
-            for (int it = 0; it < nkb; it += 3) {
-                if (it + 2 < nkb) load(it + 2, a2, b2, k2);
+            F4 a0[NAU], a1[NAU], b0[NBU], b1[NBU];
+            bool k0 = false, k1 = false;
+            int it = 0;
+            if (it < nkb) load(it, a0, b0, k0);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load(it + 1, a1, b1, k1);
                 store(it, a0, b0, k0);
-                if (it + 1 < nkb) {
-                    if (it + 3 < nkb) load(it + 3, a0, b0, k0);
+                if (more) {
+                    if (it + 2 < nkb) load(it + 2, a0, b0, k0);
                     store(it + 1, a1, b1, k1);
-                }
-                if (it + 2 < nkb) {
-                    if (it + 4 < nkb) load(it + 4, a1, b1, k1);
-                    store(it + 2, a2, b2, k2);
                 }
             }
         }

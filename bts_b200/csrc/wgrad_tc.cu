@@ -333,23 +333,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                 fence_proxy_async();
                 mbar_arrive(full(s));
             };
-            // three register buffers: the loads of TWO later k-blocks are in flight while one is split and stored.  With a
-            // single look-ahead (round 1) every k-block exposed (load latency - store time) ~ 500 cycles: the producers, not the
-            // tensor pipe, paced the wide layers (ncu: long-scoreboard stalls dominate the producer warps).
-            F4 va[NU], vb[NU], vc[NU];
-            uint32_t ma = 0, mb = 0, mc = 0;
-            if (0 < nkb) load_x(0, va, ma);
-            if (1 < nkb) load_x(1, vb, mb);
-            for (int it = 0; it < nkb; it += 3) {
-                if (it + 2 < nkb) load_x(it + 2, vc, mc);
+            F4 va[NU], vb[NU];
+            uint32_t ma = 0, mb = 0;
+            int it = 0;
+            if (it < nkb) load_x(it, va, ma);
+            for (; it < nkb; it += 2) {
+                const bool more = it + 1 < nkb;
+                if (more) load_x(it + 1, vb, mb);
                 store_x(it, va, ma);
-                if (it + 1 < nkb) {
-                    if (it + 3 < nkb) load_x(it + 3, va, ma);
+                if (more) {
+                    if (it + 2 < nkb) load_x(it + 2, va, ma);
                     store_x(it + 1, vb, mb);
-                }
-                if (it + 2 < nkb) {
-                    if (it + 4 < nkb) load_x(it + 4, vb, mb);
-                    store_x(it + 2, vc, mc);
                 }
             }
         } else {
@@ -402,20 +396,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_tc_kernel(const WgradPar
                     if (++ds_s == S) { ds_s = 0; ds_ph ^= 1; }
                 }
             };
-            F4 va[NU], vb[NU], vc[NU];                    // three buffers: two passes of loads in flight (see the x group)
+            F4 va[NU], vb[NU];
             const int nj = nkb * npass;
-            if (0 < nj) load_d(0, va);
-            if (1 < nj) load_d(1, vb);
-            for (int it = 0; it < nj; it += 3) {
-                if (it + 2 < nj) load_d(it + 2, vc);
+            int it = 0;
+            if (it < nj) load_d(it, va);
+            for (; it < nj; it += 2) {
+                const bool more = it + 1 < nj;
+                if (more) load_d(it + 1, vb);
                 store_d(it, va);
-                if (it + 1 < nj) {
-                    if (it + 3 < nj) load_d(it + 3, va);
+                if (more) {
+                    if (it + 2 < nj) load_d(it + 2, va);
                     store_d(it + 1, vb);
-                }
-                if (it + 2 < nj) {
-                    if (it + 4 < nj) load_d(it + 4, vb);
-                    store_d(it + 2, vc);
                 }
             }
         }

@@ -22,11 +22,13 @@ CASES = [
 
 @pytest.fixture
 def tma():
-    from bts_b200 import _lib
+    from bts_b200 import _lib, conv
     L = _lib.lib()
-    prev = L.bts_conv_get_tma()
+    prev, prev_cm = L.bts_conv_get_tma(), conv.CHUNK_MAJOR
+    conv.CHUNK_MAJOR = False               # TMA staging enumerates K tap-major; the chunk-major layers keep LDG producers
     yield L
     L.bts_conv_set_tma(prev)
+    conv.CHUNK_MAJOR = prev_cm
 
 
 @pytest.mark.parametrize("B,Cin,H,W,Cout,k,pad,dil,pre", CASES)

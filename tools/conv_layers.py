@@ -55,13 +55,13 @@ for name, Cin, H, W, Cout, k, dil, up in LAYERS:
     flops = 2.0 * B * Ho * Wo * Cout * Cin * k * k
     packed = conv.pack_weights(w)
     if mode == "fwd":
-        f_tc = lambda: conv.conv2d_tc(x, w, 1, pad, dil, upsample2=bool(up), packed=packed)
+        f_tc = lambda: conv.conv2d_tc(x, w, 1, pad, dil, upsample2=bool(up))
         xu = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
         f_cd = lambda: F.conv2d(xu, w, None, 1, pad, dil)
     elif mode == "dgrad":
         gy = torch.randn(B, Cout, Ho, Wo, device="cuda").contiguous(memory_format=torch.channels_last)
         packedT = conv.pack_weights(w, True)
-        f_tc = lambda: conv.conv2d_tc(gy, w, 1, dil * (k - 1) - pad, dil, packed=packedT, transpose_flip=True)
+        f_tc = lambda: conv.conv2d_tc(gy, w, 1, dil * (k - 1) - pad, dil, transpose_flip=True)
         xu = F.interpolate(x, scale_factor=2, mode="nearest") if up else x
         f_cd = lambda: torch.ops.aten.convolution_backward(gy, xu, w, None, [1, 1], [pad, pad], [dil, dil], False, [0, 0], 1, [True, False, False])
     else:
