@@ -445,7 +445,7 @@ def run_lpg_config(args):
 # each have a switch.  Before timing, a SUBPROCESS checks each against an independent computation on the GPU at hand and the
 # bench only enables what passed -- a kernel bug then costs speed and is reported in the JSON line ("selfcheck"), it does not
 # silently produce a wrong number or kill the run (a device-side trap in the child leaves this process's context intact).
-SELFCHECK_FEATURES = ["lean_issue", "epi_bnbwd", "fused_adamw"]
+SELFCHECK_FEATURES = ["lean_issue", "bn_onepass", "epi_bnbwd", "fused_adamw"]
 
 
 def selfcheck_child(enabled):
@@ -489,25 +489,28 @@ def selfcheck_child(enabled):
     else:
         print("CHECK lean_issue ok %s" % det, flush=True)
 
-    print("BEGIN epi_bnbwd", flush=True)
     import torchvision
     blk = torchvision.models.densenet._DenseBlock(3, 64, 4, 32, 0.0).to(dev).train()
     from bts_b200 import model as M
     M.adopt_convs(torch.nn.Sequential(blk))
     xin = torch.randn(2, 64, 12, 16, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
-    grads = []
-    for flag in (False, True):
-        fused.EPI_BNBWD = flag
+
+    def block_grads(epi, onepass):
+        fused.EPI_BNBWD, fused.BN_ONEPASS = epi, onepass
         for q in blk.parameters():
             q.grad = None
         xi = xin.clone().requires_grad_(True)
         out = blk(xi)
         out.square().mean().backward()
         torch.cuda.synchronize()
-        grads.append([xi.grad.clone()] + [q.grad.clone() for q in blk.parameters()])
-    worst = max(relerr(a, b) for a, b in zip(grads[1], grads[0]))
-    print("CHECK epi_bnbwd %s worst rel error %.2e vs the separate reduce pass (dense block, all gradients)"
-          % ("ok" if worst < 1e-4 else "fail", worst), flush=True)
+        return [xi.grad.clone()] + [q.grad.clone() for q in blk.parameters()]
+
+    base = block_grads(False, False)
+    for feat, epi, onepass in (("bn_onepass", False, True), ("epi_bnbwd", True, False)):
+        print("BEGIN %s" % feat, flush=True)
+        worst = max(relerr(a, b) for a, b in zip(block_grads(epi, onepass), base))
+        print("CHECK %s %s worst rel error %.2e vs the reduce + apply passes (dense block, all gradients)"
+              % (feat, "ok" if worst < 1e-4 else "fail", worst), flush=True)
 
     print("BEGIN fused_adamw", flush=True)
     from bts_b200.optim import FusedAdamW
@@ -663,8 +666,9 @@ def _run_ours(args):
             ft = torch.tensor(flags, device=dev, dtype=torch.int32)
             dist.broadcast(ft, 0)
             flags = [int(v) for v in ft.tolist()]
-        lean_ok, bnb_ok, adam_ok = [bool(v) for v in flags]
+        lean_ok, onepass_ok, bnb_ok, adam_ok = [bool(v) for v in flags]
         _lib.lib().bts_conv_set_issue_mode(1 if lean_ok else 0)
+        fused.BN_ONEPASS = fused.BN_ONEPASS and onepass_ok
         fused.EPI_BNBWD = fused.EPI_BNBWD and bnb_ok      # off by default (measured slower, bts_b200/fused.py); opt-in via env
         if not adam_ok:
             args.optimizer = "torch"

@@ -103,6 +103,10 @@ SIGNATURES = {
     "bts_bn_fold": [_i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _i, _p],
+    "bts_wgrad2_set_tma": [_i],
+    "bts_wgrad2_set_min_pixels": [_ll],
+    "bts_bn_relu_bwd_fused": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p],
+    "bts_bn_bwd_correct": [_p, _ll, _ll, _i, _p, _p, _p, _ll, _p],
     "bts_bn_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],
     "bts_bn_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _i, _p, _ll, _i, _p],
     "bts_bn_apply": [_p, _ll, _ll, _i, _p, _p, _i, _p, _ll, _p],

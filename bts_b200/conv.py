@@ -65,6 +65,9 @@ def trace_report():
 if _os.environ.get("BTS_B200_TMA") is not None:            # bring-up switch for the TMA-staged activation tiles
     _lib.lib().bts_conv_set_tma(int(_os.environ["BTS_B200_TMA"]))
 
+if _os.environ.get("BTS_B200_W2_TMA") is not None:         # 0: narrow-output wgrad producers load from global memory
+    _lib.lib().bts_wgrad2_set_tma(int(_os.environ["BTS_B200_W2_TMA"]))
+
 _pack_cache = {}   # id(weight) -> (weakref, version, data_ptr, transpose) -> packed tensor
 
 
@@ -126,13 +129,15 @@ def group_window(width, cpg):
     return _lib.lib().bts_conv_group_window(int(width), int(cpg))
 
 
-CHUNK_MAJOR = _os.environ.get("BTS_B200_CHUNK_MAJOR", "1") == "1"
+CHUNK_MAJOR = _os.environ.get("BTS_B200_CHUNK_MAJOR", "0") == "1"
 
 
 def pack_flags(weight_shape, transpose_flip=False, groups=1):
     """packing / kernel flags of a layer.  bit 0 = chunk-major K order: for multi-tap kernels whose K channels are whole
     32-channel chunks, k-blocks run (chunk, tap) with the taps innermost, so the nine shifted reads of a pixel's channel chunk
-    are consecutive and hit in L1 (the narrow 3x3 layers were L2-read-bound: every input element crossed L2 -> SM 9 times)."""
+    are consecutive and hit in L1.  Measured on B200 (profiles/r02_*): L1 hit rate 77% and L2 throughput down to 11%, but the
+    kernel time did not move (the narrow layers are bound by shared-memory bandwidth, not L2), so it is off by default
+    (BTS_B200_CHUNK_MAJOR=1 enables it; tests/test_conv_order_gpu.py keeps it correct)."""
     Cout, Cin, KH, KW = weight_shape
     if not CHUNK_MAJOR or KH * KW == 1:
         return 0

@@ -18,12 +18,17 @@ namespace {
 // Column reductions over NHWC: a 256-thread block covers up to 256 channels (64 channel quads) x `rows` pixels; with
 // fewer channels the spare threads take extra pixel rows.  Four independent 16-byte loads per tensor are in flight per
 // thread; the row groups of a block are combined in shared memory, then ONE fp64 atomic per channel per block.
-template <bool BWD>
+// MODE 0: forward statistics; 1: backward sums; 2: backward sums AND out += [y>0]*scale*g in the same pass (the part of dx
+// that does not depend on the sums -- the k1*x + k0 remainder is deferred, see bts_bn_relu_bwd_fused).
+template <int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const float *__restrict__ x, long long xs, const float *__restrict__ g,
                                                         long long gs, long long M, int C, int rows,
                                                         const float *__restrict__ scale, const float *__restrict__ shift,
                                                         const float *__restrict__ mean, const float *__restrict__ invstd,
-                                                        double *__restrict__ acc0, double *__restrict__ acc1, int relu) {
+                                                        double *__restrict__ acc0, double *__restrict__ acc1, int relu,
+                                                        float *out, long long os) {
+    constexpr bool BWD = MODE != 0;
+    constexpr bool ACC = MODE == 2;
     __shared__ float red[2][256 * 4];
     const int cchunk = min(256, C - (int)blockIdx.y * 256);
     const int tpc = (cchunk + 3) >> 2;                 // threads per pixel row
@@ -45,8 +50,9 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float *__restrict_
             }
         }
         const bool vec = (c + 3 < C) && ((xs & 3) == 0) && ((((uintptr_t)x) & 15) == 0) &&
-                         (!BWD || (((gs & 3) == 0) && ((((uintptr_t)g) & 15) == 0)));
-        auto accum = [&](const float (&xv)[4], const float (&gv)[4]) {
+                         (!BWD || (((gs & 3) == 0) && ((((uintptr_t)g) & 15) == 0))) &&
+                         (!ACC || (((os & 3) == 0) && ((((uintptr_t)out) & 15) == 0)));
+        auto accum = [&](const float (&xv)[4], const float (&gv)[4], float (&ov)[4]) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 if (!BWD) {
@@ -57,43 +63,60 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const float *__restrict_
                     const float gm = (!relu || y > 0.f) ? gv[e] : 0.f;
                     a0[e] += gm;
                     a1[e] = fmaf(gm, (xv[e] - mu[e]) * is[e], a1[e]);
+                    if (ACC) ov[e] = fmaf(sc[e], gm, ov[e]);
                 }
             }
         };
         if (vec) {
             long long m = m0;
             for (; m + 3LL * rp < m1; m += 4LL * rp) {
-                float4 q[4], r[4];
+                float4 q[4], r[4], o[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const float4 *>(x + (m + (long long)u * rp) * xs + c));
                 if (BWD) {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const float4 *>(g + (m + (long long)u * rp) * gs + c));
                 }
+                if (ACC) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) o[u] = *reinterpret_cast<const float4 *>(out + (m + (long long)u * rp) * os + c);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float xv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
                     const float gv[4] = {BWD ? r[u].x : 0.f, BWD ? r[u].y : 0.f, BWD ? r[u].z : 0.f, BWD ? r[u].w : 0.f};
-                    accum(xv, gv);
+                    float ov[4] = {ACC ? o[u].x : 0.f, ACC ? o[u].y : 0.f, ACC ? o[u].z : 0.f, ACC ? o[u].w : 0.f};
+                    accum(xv, gv, ov);
+                    if (ACC)
+                        *reinterpret_cast<float4 *>(out + (m + (long long)u * rp) * os + c) = make_float4(ov[0], ov[1], ov[2], ov[3]);
                 }
             }
             for (; m < m1; m += rp) {
                 const float4 q = __ldg(reinterpret_cast<const float4 *>(x + m * xs + c));
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (BWD) r = __ldg(reinterpret_cast<const float4 *>(g + m * gs + c));
+                if (ACC) o = *reinterpret_cast<const float4 *>(out + m * os + c);
                 const float xv[4] = {q.x, q.y, q.z, q.w};
                 const float gv[4] = {r.x, r.y, r.z, r.w};
-                accum(xv, gv);
+                float ov[4] = {o.x, o.y, o.z, o.w};
+                accum(xv, gv, ov);
+                if (ACC) *reinterpret_cast<float4 *>(out + m * os + c) = make_float4(ov[0], ov[1], ov[2], ov[3]);
             }
         } else {
             for (long long m = m0; m < m1; m += rp) {
-                float xv[4], gv[4];
+                float xv[4], gv[4], ov[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     xv[e] = c + e < C ? __ldg(x + m * xs + c + e) : 0.f;
                     gv[e] = (BWD && c + e < C) ? __ldg(g + m * gs + c + e) : 0.f;
+                    ov[e] = (ACC && c + e < C) ? out[m * os + c + e] : 0.f;
                 }
-                accum(xv, gv);
+                accum(xv, gv, ov);
+                if (ACC) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < C) out[m * os + c + e] = ov[e];
+                }
             }
         }
     }
@@ -132,6 +155,46 @@ __global__ void bn_bwd_coef_kernel(const double *__restrict__ S1, const double *
     const double k0 = -s * S1[c] / (double)N - k1 * (double)mean[c];
     coef[c] = (float)k0;
     coef[C + c] = (float)k1;
+}
+
+// deferred form: the (k0, k1) of every BatchNorm that reads channel c of a concat slab add up (dx is linear in them)
+__global__ void bn_bwd_coef_accum_kernel(const double *__restrict__ S1, const double *__restrict__ S2, long long N, int C,
+                                         const float *__restrict__ scale, const float *__restrict__ mean,
+                                         const float *__restrict__ invstd, double *__restrict__ K0, double *__restrict__ K1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s = scale[c];
+    const double k1 = -s * (double)invstd[c] * S2[c] / (double)N;
+    K1[c] += k1;
+    K0[c] += -s * S1[c] / (double)N - k1 * (double)mean[c];
+}
+
+// out[m, c] += K1[c]*x[m, c] + K0[c]
+__global__ void __launch_bounds__(256) bn_bwd_correct_kernel(const float *__restrict__ x, long long xs, long long M, int C,
+                                                             const double *__restrict__ K0, const double *__restrict__ K1,
+                                                             float *__restrict__ out, long long os) {
+    const int cq = (C + 3) >> 2;
+    const long long total = M * cq;
+    const bool vec = ((xs & 3) == 0) && ((os & 3) == 0) && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)out) & 15) == 0) &&
+                     ((C & 3) == 0);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long m = idx / cq;
+        const int c = (int)(idx - m * cq) * 4;
+        if (vec) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(x + m * xs + c));
+            float4 o = *reinterpret_cast<const float4 *>(out + m * os + c);
+            o.x += fmaf(q.x, (float)K1[c], (float)K0[c]);
+            o.y += fmaf(q.y, (float)K1[c + 1], (float)K0[c + 1]);
+            o.z += fmaf(q.z, (float)K1[c + 2], (float)K0[c + 2]);
+            o.w += fmaf(q.w, (float)K1[c + 3], (float)K0[c + 3]);
+            *reinterpret_cast<float4 *>(out + m * os + c) = o;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c + e < C) out[m * os + c + e] += fmaf(x[m * xs + c + e], (float)K1[c + e], (float)K0[c + e]);
+        }
+    }
 }
 
 __global__ void bn_finalize_kernel(const double *__restrict__ sum, const double *__restrict__ sumsq, long long N, int C,
@@ -260,8 +323,8 @@ extern "C" int bts_bn_stats(const float *x, long long x_pixel_stride, long long 
     const int cg = (C + 255) / 256;
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
-    bn_reduce_kernel<false><<<grid, 256, 0, st>>>(x, x_pixel_stride, nullptr, 0, M, C, rows, nullptr, nullptr, nullptr,
-                                                  nullptr, sum, sumsq, 0);
+    bn_reduce_kernel<0><<<grid, 256, 0, st>>>(x, x_pixel_stride, nullptr, 0, M, C, rows, nullptr, nullptr, nullptr, nullptr,
+                                              sum, sumsq, 0, nullptr, 0);
     BTS_LAUNCH_CHECK();
     return 0;
 }
@@ -296,10 +359,50 @@ extern "C" int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const
     const int cg = (C + 255) / 256;
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
-    bn_reduce_kernel<true><<<grid, 256, 0, st>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, rows, scale, shift, mean, invstd,
-                                                 S1, S2, relu);
+    bn_reduce_kernel<1><<<grid, 256, 0, st>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, rows, scale, shift, mean, invstd,
+                                              S1, S2, relu, nullptr, 0);
     BTS_LAUNCH_CHECK();
     bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(S1, S2, M, C, scale, mean, invstd, coef);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+// One-pass BatchNorm(+ReLU) backward into a concat gradient slab.  dx = [y>0]*scale*g + k1*x + k0 splits into a part that
+// needs no reduction -- accumulated into `out` by the same pass that reduces S1, S2 -- and the per-channel affine remainder,
+// which is linear in (k0, k1): K0/K1 (fp64, one entry per slab channel) collect it over every BatchNorm that reads the
+// channel, and bts_bn_bwd_correct applies the total once, just before the channel's gradient is consumed.  One streaming
+// pass over (x, g, out) per layer instead of reduce + apply.  K0 == NULL: frozen statistics (no remainder).
+extern "C" int bts_bn_relu_bwd_fused(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
+                                     long long M, int C, const float *scale, const float *shift, const float *mean,
+                                     const float *invstd, double *S1, double *S2, float *out, long long out_pixel_stride,
+                                     double *K0, double *K1, void *stream) {
+    if (!x || !g || !scale || !shift || !mean || !invstd || !S1 || !S2 || !out || M < 1 || C < 1) return BTS_EINVAL;
+    if ((K0 == nullptr) != (K1 == nullptr)) return BTS_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(S2, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    const int cg = (C + 255) / 256;
+    const int rows = reduce_rows(M, cg);
+    dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
+    bn_reduce_kernel<2><<<grid, 256, 0, st>>>(x, x_pixel_stride, g, g_pixel_stride, M, C, rows, scale, shift, mean, invstd,
+                                              S1, S2, 1, out, out_pixel_stride);
+    BTS_LAUNCH_CHECK();
+    if (K0) {
+        bn_bwd_coef_accum_kernel<<<(C + 127) / 128, 128, 0, st>>>(S1, S2, M, C, scale, mean, invstd, K0, K1);
+        BTS_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int bts_bn_bwd_correct(const float *x, long long x_pixel_stride, long long M, int C, const double *K0,
+                                  const double *K1, float *out, long long out_pixel_stride, void *stream) {
+    if (!x || !K0 || !K1 || !out || M < 1 || C < 1) return BTS_EINVAL;
+    const long long total = M * ((C + 3) / 4);
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)bts_num_sms() * 16;
+    if (grid > cap) grid = cap;
+    bn_bwd_correct_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(x, x_pixel_stride, M, C, K0, K1, out, out_pixel_stride);
     BTS_LAUNCH_CHECK();
     return 0;
 }

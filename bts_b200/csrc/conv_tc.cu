@@ -541,8 +541,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block this group loads; this lane's channel
         //      quad of that k-block is g = 8 kb + chunk -> (tap, quad in tap) by multiply-shift division
         int oy[8], ox[8], rowoff[8];
-        uint32_t tmask[8];                         // bit t: filter tap t of this row falls inside the image (taps <= 32, no up-sample)
-        const bool use_tm = (UP == 0) && taps <= 32;
         int l_ti = 0, l_kb = grp, cur_ti = -1;
         while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         auto set_tile = [&](int ti) {
@@ -589,9 +587,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int yy = oy[i] + dy, xx = ox[i] + dx;
-                bool ok;
-                if (use_tm) ok = cok && ((tmask[i] >> tap) & 1u);
-                else ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
+                bool ok = cok && (unsigned)yy < (unsigned)Hin && (unsigned)xx < (unsigned)Win;
                 if (UP == 2) ok = ok && (((yy | xx) & 1) == 0);          // zero-stuffed source: odd coordinates are zeros
                 mk |= (ok ? 1u : 0u) << i;
                 int off;
@@ -644,48 +640,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             // hi = fp32 rounded to tf32 (round-half-away on the 13 dropped bits, 2 integer ops); lo = x - hi is exact in fp32
             // and the tensor core reads its top 19 bits.  (Truncating instead of rounding saves one op per element but
             // makes lo one-signed: the dropped lo*lo term and lo's own truncation then add up coherently over K -- measured
-            // 2-3x the error, past the 2e-5 bar of tests/test_conv_gpu.py -- so the rounding stays.)
-            auto split4 = [&](const float (&a)[4], uint32_t row_off) {
+            // 2-3x the error, past the 2e-5 bar of tests/test_conv_gpu.py -- so the rounding stays.  A per-tile tap-mask +
+            // select-free interior path was also measured: more registers -> spills, fwd 27 -> 34 ms per K16 step.)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool live = (mask >> i) & 1u;
                 float hi[4], lo[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    hi[e] = __uint_as_float((__float_as_uint(a[e]) + 0x1000u) & 0xffffe000u);
-                    lo[e] = a[e] - hi[e];
-                }
-                st_shared_v4(a_hi + row_off, hi[0], hi[1], hi[2], hi[3]);
-                st_shared_v4(a_lo + row_off, lo[0], lo[1], lo[2], lo[3]);
-            };
-            if (AFF && mask == 0xffu) {
-                // interior rows (no tap in the padding): no per-element select
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float a[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        a[e] = fmaf(v[i].v[e], sc[e], sh[e]);
-                        if (RELU) a[e] = fmaxf(a[e], 0.f);
+                    float a = v[i].v[e];
+                    if (AFF) {
+                        a = fmaf(a, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
+                        if (RELU) a = fmaxf(a, 0.f);
+                        a = live ? a : 0.f;                     // zero padding is applied after the pre-op
+                    } else if (RELU) {
+                        a = fmaxf(a, 0.f);                      // padded lanes were loaded as 0
                     }
-                    split4(a, (uint32_t)i * 2048u);
+                    const float h = __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+                    hi[e] = h;
+                    lo[e] = a - h;
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool live = (mask >> i) & 1u;
-                    float a[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float t = v[i].v[e];
-                        if (AFF) {
-                            t = fmaf(t, sc[e], sh[e]);              // scale/shift are 0 beyond Cin
-                            if (RELU) t = fmaxf(t, 0.f);
-                            t = live ? t : 0.f;                     // zero padding is applied after the pre-op
-                        } else if (RELU) {
-                            t = fmaxf(t, 0.f);                      // padded lanes were loaded as 0
-                        }
-                        a[e] = t;
-                    }
-                    split4(a, (uint32_t)i * 2048u);
-                }
+                st_shared_v4(a_hi + (uint32_t)i * 2048u, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(a_lo + (uint32_t)i * 2048u, lo[0], lo[1], lo[2], lo[3]);
             }
             fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
             mbar_arrive(bar_full);

@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const void *tmap, in
         "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"(off_w), "h"(off_h)
         : "memory");
 }
+// plain (tiled) 2-D tensor load: coordinates {c0 = innermost, c1}; out-of-range elements are zero-filled
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

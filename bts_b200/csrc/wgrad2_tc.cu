@@ -9,6 +9,17 @@
 // block: per k-block of 16 input pixels the activation tile is produced once and multiplied against the 9 shifted dY
 // tiles (cheap: <= 48 channels each), accumulating into 9 column blocks of TMEM (9 x 48 = 432 of 512 columns).
 // Same MN-major SWIZZLE_128B_BASE32B operand tiles and deterministic split-K partial layout as wgrad_tc.cu.
+//
+// Operand staging (round 2): the 9 shifted dY windows of a k-block overlap -- they are KH row segments of 16 + (KW-1)*dil
+// consecutive output pixels -- and ncu showed the producers 58% stalled on the scoreboard of their global loads (one k-block
+// of register prefetch, L1 hit rate 13%).  With TMA = true a loader lane copies the raw fp32 segments (and the raw x tile
+// unless it is read through the nearest-neighbour up-sample) into a small landing ring, several k-blocks ahead
+// (cp.async.bulk.tensor.2d, no swizzle, zero fill past the tensor ends); the producers then read shared memory, apply the
+// border masks / pre-op, split hi/lo and write the swizzled operand tiles as before.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -24,6 +35,8 @@ constexpr int MAX_STAGES = 4;
 constexpr int NUM_THREADS = 576;               // 2 control warps + 16 producer warps (4 quarters of 128 threads)
 constexpr int PRODUCERS = 512;
 constexpr int SMEM_BUDGET = 224 * 1024;
+constexpr int MAX_RING = 4;                  // landing-ring slots (TMA staging)
+constexpr int X_RAW_BYTES = KP * BLOCK_CI * 4;   // raw x tile of a k-block: 8 KB
 
 struct W2Params {
     const float *x; long long xs;
@@ -39,16 +52,20 @@ struct W2Params {
     int Mq;                  // B*Hin*Win input pixels
     int stages, stage_bytes, precision;
     int legacy;              // 1: round-1 single-lane MMA issue loop (fallback switch)
+    // TMA landing ring (TMA = true): slot = [raw x tile 8 KB (unless up) | KH segments of segw pixels x cg channels]
+    int ring, slot_bytes, seg_bytes, segw, tox_max, slot_tx;
 };
 
-template <int PRE, bool UP, bool VEC>
-__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Params p) {
+template <int PRE, bool UP, bool VEC, bool TMA>
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Params p, const __grid_constant__ CUtensorMap tmx,
+                                                                   const __grid_constant__ CUtensorMap tmd) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
     const int taps = p.KH * p.KW;
     const int S = p.stages;
-    const uint32_t pre_off = (uint32_t)S * (uint32_t)p.stage_bytes;
+    const uint32_t ring_off = (uint32_t)S * (uint32_t)p.stage_bytes;
+    const uint32_t pre_off = ring_off + (TMA ? (uint32_t)p.ring * (uint32_t)p.slot_bytes : 0u);
     float *s_scale = reinterpret_cast<float *>(sm + pre_off);
     float *s_shift = s_scale + BLOCK_CI;
     const uint32_t bar0 = base + pre_off + 2 * BLOCK_CI * 4;
@@ -56,7 +73,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
     const uint32_t accum_full = bar0 + 8u * (2 * MAX_STAGES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
+    auto rfull = [&](int j) { return bar0 + 8u * (2 * MAX_STAGES + 1 + j); };
+    auto rempty = [&](int j) { return bar0 + 8u * (2 * MAX_STAGES + 1 + MAX_RING + j); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1 + 2 * MAX_RING);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci_tile = blockIdx.x, cgi = blockIdx.y, split = blockIdx.z;
@@ -79,6 +98,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             mbar_init(empty(s), 1);
         }
         mbar_init(accum_full, 1);
+        for (int j = 0; j < MAX_RING; ++j) {
+            mbar_init(rfull(j), 1);
+            mbar_init(rempty(j), PRODUCERS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -97,7 +120,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 1) {
+    if (TMA && warp == 0) {
+        // ---- loader: one lane keeps the landing ring `ring` k-blocks ahead of the producers
+        if (lane == 0) {
+            if (!UP) tma_prefetch_desc(&tmx);
+            tma_prefetch_desc(&tmd);
+            int j = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(rempty(j), ph ^ 1);
+                const uint32_t dst = base + ring_off + (uint32_t)j * (uint32_t)p.slot_bytes;
+                const int q0 = (kb0 + it) * KP;
+                mbar_arrive_expect_tx(rfull(j), (uint32_t)p.slot_tx);
+                uint32_t seg = dst;
+                if (!UP) {
+                    tma_tile_2d(dst, &tmx, ci_tile * BLOCK_CI, q0, rfull(j));
+                    seg += X_RAW_BYTES;
+                }
+                for (int ky = 0; ky < p.KH; ++ky)     // output pixels q - (ky*dil - pad)*W - tox, tox <= tox_max
+                    tma_tile_2d(seg + (uint32_t)ky * (uint32_t)p.seg_bytes, &tmd, co0,
+                                q0 - (ky * p.dil - p.pad) * p.Wout - p.tox_max, rfull(j));
+                if (++j == p.ring) { j = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
         // MMA issuer: whole warp in the loop, one elected lane issues (see conv_tc.cu: the round-1 single-lane loops paid
         // ~4 cycles x hundreds of issue-warp instructions per k-block).  With the taps packed along N the three products
         // of a k-group are 3 x ceil(taps*ncol/256) instructions instead of 3 x taps.
@@ -221,13 +267,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         constexpr int NBU = 6;                     // dY units per thread per k-block: <= 3 taps x 2 chunks
         constexpr int NAU = 1;                     // x units per thread per k-block
         // tap offsets of this thread's taps (t = half, half+4, half+8), computed once: no divisions in the k-loop
-        int toy[NBU / 2], tox[NBU / 2];
+        int toy[NBU / 2], tox[NBU / 2], tky[NBU / 2];
 #pragma unroll
         for (int j = 0; j < NBU / 2; ++j) {
             const int t = half + 4 * j;
             const int ky = t / p.KW, kx = t - ky * p.KW;
             toy[j] = ky * p.dil - p.pad;
             tox[j] = kx * p.dil - p.pad;
+            tky[j] = ky < p.KH ? ky : 0;
         }
         // shared-memory offsets of this thread's dY units in the densely packed tile: N slot = t*ncol + channel
         uint32_t boff[NBU];
@@ -242,12 +289,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                 blive[j * 2 + ch] = t < taps && ch < nb && c < ncol;
                 boff[j * 2 + ch] = (uint32_t)(n >> 5) * CHUNK + mn_swizzle_off(row, (n & 31) >> 2);
             }
-        auto load = [&](int it, F4(&va)[NAU], F4(&vb)[NBU], bool &okx) {
+        struct Cursor { int qx, qy, qb; };
+        Cursor cur = {qx, qy, qb};
+        auto advance = [&](Cursor &c) {
+            c.qx += KP;
+            while (c.qx >= p.Win) {
+                c.qx -= p.Win;
+                if (++c.qy == p.Hin) { c.qy = 0; ++c.qb; }
+            }
+        };
+        // ---- x~ tile through the load path: this thread's pixel, channels of its chunk
+        auto load_x = [&](int it, const Cursor &c_, F4(&va)[NAU], bool &okx) {
             const int q = (kb0 + it) * KP + row;
             okx = q < p.Mq;
-            // ---- x~ tile: this thread's pixel, channels of its two chunks
-            const int sy = UP ? (qy >> 1) : qy, sx = UP ? (qx >> 1) : qx;
-            const int xoff = ((qb * p.Hs + sy) * p.Ws + sx) * xs;
+            const int sy = UP ? (c_.qy >> 1) : c_.qy, sx = UP ? (c_.qx >> 1) : c_.qx;
+            const int xoff = ((c_.qb * p.Hs + sy) * p.Ws + sx) * xs;
 #pragma unroll
             for (int ch = 0; ch < NAU; ++ch) {
                 const int c = cbx + ch * 32;
@@ -270,13 +326,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                     }
                 }
             }
-            // ---- shifted dY tiles: taps t = half, half+2, ...; output pixel (qy - dy_t, qx - dx_t)
+        };
+        // ---- shifted dY tiles through the load path: taps t = half, half+4, ...; output pixel (qy - dy_t, qx - dx_t)
+        auto load_d = [&](const Cursor &c_, bool okx, F4(&vb)[NBU]) {
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
                 const int t = half + 4 * j;
-                const int py = qy - toy[j], px = qx - tox[j];
+                const int py = c_.qy - toy[j], px = c_.qx - tox[j];
                 const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
-                const int doff = ((qb * p.Hout + py) * p.Wout + px) * dys;
+                const int doff = ((c_.qb * p.Hout + py) * p.Wout + px) * dys;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const int c = cbd + ch * 32;
@@ -301,11 +359,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                     }
                 }
             }
-            qx += KP;
-            while (qx >= p.Win) {
-                qx -= p.Win;
-                if (++qy == p.Hin) { qy = 0; ++qb; }
+        };
+        auto load = [&](int it, F4(&va)[NAU], F4(&vb)[NBU], bool &okx) {
+            load_x(it, cur, va, okx);
+            load_d(cur, okx, vb);
+            advance(cur);
+        };
+        // ---- the same operands out of a landing-ring slot (TMA): raw x tile [16 px][128 ch], then KH segments [segw px][cg ch]
+        auto ring_read = [&](int it, uint32_t slot, F4(&va)[NAU], F4(&vb)[NBU], bool &okx) {
+            const int q = (kb0 + it) * KP + row;
+            okx = q < p.Mq;
+            uint32_t segb = slot;
+            if (!UP) {
+                const float4 v = ld_shared_v4(slot + (uint32_t)((row * BLOCK_CI + half * 32 + unit * 4) * 4));
+                va[0].v[0] = v.x; va[0].v[1] = v.y; va[0].v[2] = v.z; va[0].v[3] = v.w;    // channels >= Cin, pixels >= Mq: zero fill
+                segb += X_RAW_BYTES;
             }
+#pragma unroll
+            for (int j = 0; j < NBU / 2; ++j) {
+                const int t = half + 4 * j;
+                const int py = cur.qy - toy[j], px = cur.qx - tox[j];
+                const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
+                const uint32_t rowb = segb + (uint32_t)tky[j] * (uint32_t)p.seg_bytes +
+                                      (uint32_t)((row + p.tox_max - tox[j]) * p.cg + unit * 4) * 4u;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    F4 &dst = vb[j * 2 + ch];
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (okd && blive[j * 2 + ch]) v = ld_shared_v4(rowb + (uint32_t)ch * 128u);
+                    dst.v[0] = v.x; dst.v[1] = v.y; dst.v[2] = v.z; dst.v[3] = v.w;
+                }
+            }
+            advance(cur);
         };
         auto split_store = [&](uint32_t hi_addr, uint32_t lo_addr, const F4 &v) {
             float hi[4], lo[4];
@@ -355,7 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             fence_proxy_async();
             mbar_arrive(full(s));
         };
-        {
+        if constexpr (!TMA) {
             F4 a0[NAU], a1[NAU], b0[NBU], b1[NBU];
             bool k0 = false, k1 = false;
             int it = 0;
@@ -367,6 +452,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                 if (more) {
                     if (it + 2 < nkb) load(it + 2, a0, b0, k0);
                     store(it + 1, a1, b1, k1);
+                }
+            }
+        } else {
+            // consume the landing ring; an up-sampled x still comes through the load path, one k-block ahead (own cursor)
+            F4 xc[NAU], xn[NAU], va[NAU], vb[NBU];
+            bool kc = false, kn = false, okx = false;
+            Cursor pre = cur;
+            if (UP && nkb > 0) { load_x(0, pre, xc, kc); advance(pre); }
+            int rj = 0;
+            uint32_t rph = 0;
+            for (int it = 0; it < nkb; ++it) {
+                if (UP && it + 1 < nkb) { load_x(it + 1, pre, xn, kn); advance(pre); }
+                mbar_wait(rfull(rj), rph);
+                ring_read(it, base + ring_off + (uint32_t)rj * (uint32_t)p.slot_bytes, va, vb, okx);
+                mbar_arrive(rempty(rj));               // the slot's values are in registers: the loader may refill it
+                if (++rj == p.ring) { rj = 0; rph ^= 1; }
+                if (UP) {
+                    store(it, xc, vb, okx);
+#pragma unroll
+                    for (int ch = 0; ch < NAU; ++ch) xc[ch] = xn[ch];
+                    kc = kn;
+                } else {
+                    store(it, va, vb, okx);
                 }
             }
         }
@@ -423,9 +531,12 @@ int bts_wgrad2_cg(int Cout, int taps) {
 
 // measured (B200, K16 shapes): wins for Cout <= 48 on maps of >= 60k pixels (dense 3x3 of blocks 1-2, conv1, upconv1);
 // loses for Cout = 64 (two co groups re-produce the activation tile) and on the small maps of blocks 3-4
+static long long g_w2_min_pixels = 60000;
+extern "C" int bts_wgrad2_set_min_pixels(long long n) { g_w2_min_pixels = n < 0 ? 60000 : n; return 0; }
+
 bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq) {
     const int taps = KH * KW;
-    return taps > 1 && taps <= MAX_TAPS && Cout <= 64 && stride == 1 && Mq >= 60000 && bts_wgrad2_cg(Cout, taps) > 0;
+    return taps > 1 && taps <= MAX_TAPS && Cout <= 64 && stride == 1 && Mq >= g_w2_min_pixels && bts_wgrad2_cg(Cout, taps) > 0;
 }
 
 void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK) {
@@ -449,6 +560,41 @@ void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW,
     }
     *splitK = (int)split;
 }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [pixels][channels] fp32 view with a pixel stride (channel slices of slabs are fine); box = box_c channels x box_p pixels
+static bool make_rows_map(CUtensorMap *map, const float *base, long long pixel_stride, int channels, long long pixels, int box_c,
+                          int box_p) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || box_c > 256 || box_p > 256) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)channels, (cuuint64_t)pixels};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pixel_stride * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_p};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_w2_tma = 1;       // 1 (default): landing ring where eligible; 0: producers load from global memory
+extern "C" int bts_wgrad2_set_tma(int on) { g_w2_tma = on ? 1 : 0; return 0; }
 
 int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int up, int Cin, int KH, int KW, int pad,
                       int dil, const float *pre_scale, const float *pre_shift, int pre_relu, const float *dy,
@@ -476,26 +622,58 @@ int bts_wgrad2_launch(const float *x, long long xs, int B, int Hs, int Ws, int u
     if (p.stages < 2) return BTS_EINVAL;
     p.precision = precision;
     p.legacy = bts_issue_legacy();
-    const int smem = p.stages * p.stage_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
-    dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.cg - 1) / p.cg, splitK);
     const int pre = (pre_scale ? 2 : 0) | (pre_relu ? 1 : 0);
     const bool vec = bts_aligned16(x) && (xs % 4 == 0) && bts_aligned16(dy) && (dys % 4 == 0);
+    // ---- landing ring (TMA): 'same' convolutions with <= 3 kernel rows; 3 operand stages if >= 3 ring slots still fit, else 2
+    CUtensorMap tmx, tmd;
+    memset(&tmx, 0, sizeof(tmx));
+    memset(&tmd, 0, sizeof(tmd));
+    bool tma = false;
+    p.ring = p.slot_bytes = p.seg_bytes = p.segw = p.tox_max = p.slot_tx = 0;
+    if (g_w2_tma && vec && KH <= 3 && Hout == p.Hin && Wout == p.Win) {
+        p.segw = KP + (KW - 1) * dil;
+        p.tox_max = (KW - 1) * dil - pad;
+        p.seg_bytes = (p.segw * p.cg * 4 + 127) / 128 * 128;
+        p.slot_bytes = (up ? 0 : X_RAW_BYTES) + KH * p.seg_bytes;
+        p.slot_tx = (up ? 0 : X_RAW_BYTES) + KH * p.segw * p.cg * 4;
+        int st_try = p.stages > 3 ? 3 : p.stages;
+        for (; st_try >= 2 && !tma; --st_try) {
+            const int ring = (SMEM_BUDGET - st_try * p.stage_bytes) / p.slot_bytes;
+            if (ring >= 3 || (st_try == 2 && ring >= 2)) {
+                p.stages = st_try;
+                p.ring = ring > MAX_RING ? MAX_RING : ring;
+                tma = true;
+            }
+        }
+        if (tma && p.segw <= 256)
+            tma = make_rows_map(&tmd, dy, dys, Cout, (long long)B * Hout * Wout, p.cg, p.segw) &&
+                  (up || make_rows_map(&tmx, x, xs, Cin, Mq, BLOCK_CI, KP));
+        else
+            tma = false;
+        if (!tma) {
+            p.ring = 0;
+            p.stages = SMEM_BUDGET / p.stage_bytes > MAX_STAGES ? MAX_STAGES : SMEM_BUDGET / p.stage_bytes;
+        }
+    }
+    const int smem = p.stages * p.stage_bytes + p.ring * p.slot_bytes + 2 * BLOCK_CI * 4 + 256 + 1024;
+    dim3 grid((Cin + BLOCK_CI - 1) / BLOCK_CI, (Cout + p.cg - 1) / p.cg, splitK);
     cudaError_t err = cudaSuccess;
-#define BTS_LAUNCH(PRE, UP, VEC)                                                                                      \
+#define BTS_LAUNCH(PRE, UP, VEC, TMA)                                                                                 \
     do {                                                                                                              \
-        static int attr_smem_[BTS_MAX_DEVICES] = {}; int &attr_smem = attr_smem_[bts_cur_device()];                                                                                   \
+        static int attr_smem_[BTS_MAX_DEVICES] = {}; int &attr_smem = attr_smem_[bts_cur_device()];                   \
         if (attr_smem < smem) {                                                                                       \
-            err = cudaFuncSetAttribute(wgrad2_tc_kernel<PRE, UP, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+            err = cudaFuncSetAttribute(wgrad2_tc_kernel<PRE, UP, VEC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        SMEM_BUDGET + 2 * BLOCK_CI * 4 + 256 + 1024);                                  \
             if (err != cudaSuccess) return (int)err;                                                                  \
             attr_smem = SMEM_BUDGET + 2 * BLOCK_CI * 4 + 256 + 1024;                                                  \
         }                                                                                                             \
-        wgrad2_tc_kernel<PRE, UP, VEC><<<grid, NUM_THREADS, smem, st>>>(p);                                           \
+        wgrad2_tc_kernel<PRE, UP, VEC, TMA><<<grid, NUM_THREADS, smem, st>>>(p, tmx, tmd);                            \
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                                                     \
     do {                                                                                         \
-        if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true); else BTS_LAUNCH(PRE, true, false); }   \
-        else { if (vec) BTS_LAUNCH(PRE, false, true); else BTS_LAUNCH(PRE, false, false); }      \
+        if (tma) { if (p.up) BTS_LAUNCH(PRE, true, true, true); else BTS_LAUNCH(PRE, false, true, true); } \
+        else if (p.up) { if (vec) BTS_LAUNCH(PRE, true, true, false); else BTS_LAUNCH(PRE, true, false, false); }   \
+        else { if (vec) BTS_LAUNCH(PRE, false, true, false); else BTS_LAUNCH(PRE, false, false, false); }      \
     } while (0)
     switch (pre) {
         case 0: BTS_DISPATCH_UV(0); break;

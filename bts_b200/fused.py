@@ -86,6 +86,38 @@ def bn_relu_backward(x, g, st, use_stats, out, accumulate):
     return S
 
 
+# One-pass norm1 backward of a dense layer: the sums-independent part of dx is accumulated into the gradient slab by the
+# reduce pass itself, the per-channel affine remainder is summed over layers in K and applied to each growth slice right
+# before that slice is consumed (bts_bn_relu_bwd_fused / bts_bn_bwd_correct).  BTS_B200_BN_ONEPASS=0 -> reduce + apply.
+BN_ONEPASS = os.environ.get("BTS_B200_BN_ONEPASS", "1") == "1"
+
+
+def bn_relu_backward_onepass(x, g, st, out, K):
+    """out += [y>0]*scale*g ; K += (k0, k1) (K None: frozen statistics); returns (S1, S2) fp64 [2,C]"""
+    x, xs = _view(x)
+    g, gs = _view(g)
+    out, os_ = _view(out)
+    B, C, H, W = x.shape
+    M = B * H * W
+    S = torch.empty((2, C), device=x.device, dtype=torch.float64)
+    _lib.check(_lib.lib().bts_bn_relu_bwd_fused(_ptr(x), xs, _ptr(g), gs, M, C, _ptr(st[0]), _ptr(st[1]), _ptr(st[2]),
+                                                _ptr(st[3]), _ptr(S[0]), _ptr(S[1]), _ptr(out), os_,
+                                                _ptr(K[0]) if K is not None else None,
+                                                _ptr(K[1]) if K is not None else None, _stream()), "bts_bn_relu_bwd_fused")
+    _lib.count(2 if K is not None else 1)
+    return S
+
+
+def bn_backward_correct(x, K, out):
+    """out += K[1]*x + K[0] per channel (the deferred remainder of the one-pass BatchNorm backward)"""
+    x, xs = _view(x)
+    out, os_ = _view(out)
+    B, C, H, W = x.shape
+    _lib.check(_lib.lib().bts_bn_bwd_correct(_ptr(x), xs, B * H * W, C, _ptr(K[0]), _ptr(K[1]), _ptr(out), os_, _stream()),
+               "bts_bn_bwd_correct")
+    _lib.count()
+
+
 # BatchNorm-backward sums reduced in the dgrad epilogue (bts_conv_fwd_bnbwd) instead of a separate pass.  Measured on B200
 # (profiles/r02_*): the four epilogue warps already pace the short-K dgrads, and the extra strided reads of x + the
 # per-channel parameters doubled their time (dgrad 20.0 -> 33.4 ms per K16 step against 7.4 ms of reduce passes saved), so the
@@ -173,12 +205,17 @@ class _DenseBlockFn(torch.autograd.Function):
         G = gout.clone(memory_format=torch.channels_last)      # owned: the concat fan-out accumulates into it in place
         grads = [None] * len(params)
         need = ctx.needs_input_grad[3:]
+        onepass = BN_ONEPASS and not EPI_BNBWD
+        K = torch.zeros((2, slab.shape[1]), device=slab.device, dtype=torch.float64) if (onepass and training) else None
         for li in reversed(range(nl)):
             C = C0 + growth * li
             g1, b1, w1, g2, b2, w2 = params[6 * li:6 * li + 6]
             st1, st2 = sts[2 * li], sts[2 * li + 1]
             b = bs[li]
             g_out = G[:, C:C + growth]
+            if K is not None and li + 1 < nl:
+                # every later layer read these channels: their deferred k1*x + k0 terms land now, before g_out is used
+                bn_backward_correct(slab[:, C:C + growth], K[:, C:C + growth], g_out)
             # ---- conv2 (3x3) backward
             if need[6 * li + 5]:
                 grads[6 * li + 5] = conv.wgrad_tc(b, g_out, w2.shape, w2.stride(), 1, 1, 1, pre_scale=st2[0],
@@ -203,11 +240,16 @@ class _DenseBlockFn(torch.autograd.Function):
                 _, S = dgrad_bn_relu_backward(g_a2, w1, 0, 1, xin, st1, training, out=G[:, :C], accumulate=True)
             else:
                 g_a1 = conv.conv2d_tc(g_a2, w1, 1, 0, 1, transpose_flip=True)
-                S = bn_relu_backward(xin, g_a1, st1, training, G[:, :C], True)
+                if onepass:
+                    S = bn_relu_backward_onepass(xin, g_a1, st1, G[:, :C], K)
+                else:
+                    S = bn_relu_backward(xin, g_a1, st1, training, G[:, :C], True)
             if need[6 * li + 0]:
                 grads[6 * li + 0] = S[1].float()
             if need[6 * li + 1]:
                 grads[6 * li + 1] = S[0].float()
+        if K is not None and ctx.needs_input_grad[0]:
+            bn_backward_correct(slab[:, :C0], K[:, :C0], G[:, :C0])
         gx = G[:, :C0] if ctx.needs_input_grad[0] else None
         return (gx, None, None) + tuple(grads)
 

@@ -144,6 +144,11 @@ int bts_conv_get_tma(void);
 /* MMA issue loops of the three tensor-core kernels: 1 (default) = whole-warp loop with one elected lane, one barrier per stage,
  * incrementally advanced descriptors; 0 = the round-1 single-lane loops, kept as a bring-up fallback.  Process-wide. */
 int bts_conv_set_issue_mode(int lean);
+/* Tuning / bring-up switches of the narrow-output wgrad (csrc/wgrad2_tc.cu).  set_tma(0): the producers load the operands
+ * from global memory (round-1 path) instead of the TMA landing ring; set_min_pixels(n): smallest map (input pixels) routed to
+ * this kernel (default 60000, n < 0 restores it; tests pass 0 to reach it with small shapes). */
+int bts_wgrad2_set_tma(int on);
+int bts_wgrad2_set_min_pixels(long long n);
 
 /* dgrad (or any act-free conv) whose epilogue also reduces the BatchNorm(+ReLU)-backward sums of the layer in front of the
  * conv: the tile written is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat (zero them first),
@@ -226,6 +231,17 @@ int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, 
 int bts_bn_bwd_apply(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride, long long M,
                      int C, const float *scale, const float *shift, const float *coef, int relu, float *out,
                      long long out_pixel_stride, int accumulate, void *stream);
+
+/* One-pass BatchNorm+ReLU backward into a concat gradient slab (the dense-block fan-out, torchvision densenet.py
+ * _DenseLayer / _DenseBlock backward): out += [y>0]*scale*g in the same pass that reduces S1, S2; the per-channel affine
+ * remainder k1*x + k0 is added into K0/K1 (fp64, K0 == K1 == NULL for frozen statistics) and applied later, once per
+ * channel slice, by bts_bn_bwd_correct (out += K1*x + K0) -- before that slice's gradient is consumed. */
+int bts_bn_relu_bwd_fused(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride, long long M,
+                          int C, const float *scale, const float *shift, const float *mean, const float *invstd,
+                          double *S1, double *S2, float *out, long long out_pixel_stride, double *K0, double *K1,
+                          void *stream);
+int bts_bn_bwd_correct(const float *x, long long x_pixel_stride, long long M, int C, const double *K0, const double *K1,
+                       float *out, long long out_pixel_stride, void *stream);
 
 /* ---- streaming NHWC glue kernels of the decoder / encoder transitions (csrc/elem.cu) ---------------------------
  * All take explicit pixel strides (floats) so channel slices of wider slabs are read / written in place.

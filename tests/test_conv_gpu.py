@@ -138,12 +138,29 @@ def test_single_output_channel_head_kernels(C, K, sig):
     assert (wc.grad.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max() < 1e-5
 
 
+@pytest.fixture(params=["tma_ring", "global_loads", "auto_small_map"])
+def w2_mode(request):
+    """routes small test shapes to the shifted-dY kernel (its production threshold is 60k pixels) with the operands staged
+    through the TMA landing ring or loaded by the producers; 'auto_small_map' leaves the production routing (wgrad_tc)"""
+    from bts_b200 import _lib
+    L = _lib.lib()
+    if request.param != "auto_small_map":
+        L.bts_wgrad2_set_min_pixels(0)
+        L.bts_wgrad2_set_tma(1 if request.param == "tma_ring" else 0)
+    yield request.param
+    L.bts_wgrad2_set_min_pixels(-1)
+    L.bts_wgrad2_set_tma(1)
+
+
 @pytest.mark.parametrize("Cin,Cout,H,W,dil,up,pre", [(192, 48, 9, 11, 1, False, True), (36, 32, 10, 13, 1, False, False),
                                                      (64, 32, 6, 7, 1, True, False), (161, 64, 8, 9, 1, False, False),
-                                                     (40, 24, 7, 5, 3, False, True)])
-def test_wgrad_narrow_output_shifted_dy_kernel(Cin, Cout, H, W, dil, up, pre):
+                                                     (40, 24, 7, 5, 3, False, True), (192, 48, 16, 32, 1, False, True),
+                                                     (64, 32, 5, 8, 1, True, True), (128, 64, 12, 16, 1, True, False),
+                                                     (36, 32, 33, 47, 1, False, False)])
+def test_wgrad_narrow_output_shifted_dy_kernel(w2_mode, Cin, Cout, H, W, dil, up, pre):
     """Cout <= 64, 3x3: the all-taps-in-one-CTA wgrad (wgrad2_tc.cu) incl. fused BN+ReLU prologue, nearest-x2
-    up-sampling, dilation, odd channel counts (scalar-load path) -- vs torch fp64 autograd."""
+    up-sampling, dilation, odd channel counts (scalar-load path), k-blocks that straddle image rows and images -- vs torch
+    fp64 autograd."""
     from bts_b200 import conv
     g = torch.Generator().manual_seed(Cin + Cout)
     x = torch.randn(2, Cin, H, W, generator=g)

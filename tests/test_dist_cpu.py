@@ -42,13 +42,16 @@ def test_flat_gradient_allreduce_matches_mean_of_shard_gradients():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    import socket
+    with socket.socket() as sk:                 # a port that is free right now (a fixed one can clash with another job)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
     for p in procs:
-        p.join(60)
+        p.join(120)
         assert p.exitcode == 0
     # expected: mean over ranks of the gradient each shard produces on its own
     g = torch.Generator().manual_seed(1)

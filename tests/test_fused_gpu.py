@@ -22,15 +22,18 @@ def _block(C0, L, growth=48, bn_size=4):
     return blk
 
 
-@pytest.fixture(params=[False, True], ids=["bn_reduce_pass", "bn_sums_in_dgrad_epilogue"])
+@pytest.fixture(params=["onepass", "reduce_apply", "epilogue"],
+                ids=["bn_one_pass_deferred_affine", "bn_reduce_then_apply", "bn_sums_in_dgrad_epilogue"])
 def epi_bnbwd(request):
-    """both forms of the BatchNorm backward: separate streaming reduce pass (default) and the sums reduced in the dgrad
-    epilogue (bts_conv_fwd_bnbwd)"""
+    """the three forms of the dense-layer BatchNorm backward: one streaming pass with the per-channel affine remainder
+    deferred (default, bts_bn_relu_bwd_fused + bts_bn_bwd_correct), reduce pass + apply pass, and the sums reduced in the
+    dgrad epilogue (bts_conv_fwd_bnbwd)"""
     from bts_b200 import fused
-    prev = fused.EPI_BNBWD
-    fused.EPI_BNBWD = request.param
+    prev = fused.EPI_BNBWD, fused.BN_ONEPASS
+    fused.EPI_BNBWD = request.param == "epilogue"
+    fused.BN_ONEPASS = request.param == "onepass"
     yield request.param
-    fused.EPI_BNBWD = prev
+    fused.EPI_BNBWD, fused.BN_ONEPASS = prev
 
 
 @pytest.mark.parametrize("mode", ["train", "eval"])
