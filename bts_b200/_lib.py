@@ -86,6 +86,7 @@ SIGNATURES = {
     "bts_conv_set_tma": [_i],
     "bts_conv_get_tma": [],
     "bts_conv_set_issue_mode": [_i],
+    "bts_conv_set_producer_groups": [_i],
     "bts_conv_group_window": [_i, _i],
     "bts_conv_packed_floats_grouped": [_i, _i, _i, _i],
     "bts_conv_pack_weights_grouped": [_p, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _p, _p],
@@ -105,6 +106,8 @@ SIGNATURES = {
     "bts_bn_relu_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _i, _p],
     "bts_wgrad2_set_tma": [_i],
     "bts_wgrad2_set_min_pixels": [_ll],
+    "bts_wgrad2_set_min_kblocks": [_i],
+    "bts_wgrad2_set_pointwise": [_i],
     "bts_bn_relu_bwd_fused": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p],
     "bts_bn_bwd_correct": [_p, _ll, _ll, _i, _p, _p, _p, _ll, _p],
     "bts_bn_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],

@@ -225,8 +225,13 @@ constexpr int STAT_BYTES = 2 * MAX_N * 4;   // per-CTA fp32 partial sums of the 
 // bounds arithmetic, one shared store instead of two: ~2.8x fewer producer instructions per k-block.  K is enumerated per
 // tap in 32-channel chunks (identical to the dense-quad order whenever the K channels are a multiple of 32, which the
 // host requires), stride 1, no up-sample.
-template <int PRE, int UP, bool VEC, bool TMA>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+// G: producer groups (4 warps each).  G = 2 keeps one k-block of register prefetch per thread (two F4[8] buffers).  G = 4
+// (narrow-N layers, where ncu showed the MMA warp waiting on `full` with the schedulers issuing on only 48% of the cycles
+// and two producer warps per scheduler stalled on their own dependency chains) drops the second buffer -- 4 producer warps
+// per scheduler, the other groups' work hides a group's load latency -- to fit 704 threads in the register file.
+template <int PRE, int UP, bool VEC, bool TMA, int G>
+__global__ void __launch_bounds__(192 + 128 * G, 1) conv_tc_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int NUM_THREADS = 192 + 128 * G;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 (SWIZZLE_128B atoms)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -446,10 +451,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
             }
         }
         }   // lean issue loop
-    } else if (warp < 10) {
-        // ===================== activation producers (2 groups x 4 warps) =====================
+    } else if (warp < 2 + 4 * G) {
+        // ===================== activation producers (G groups x 4 warps) =====================
         const int pt = threadIdx.x - 64;           // 0..255
-        const int grp = pt >> 7;                   // producer group: global k-blocks gk == grp (mod 2)
+        const int grp = pt >> 7;                   // producer group: global k-blocks gk == grp (mod G)
         const int t = pt & 127;
         const int chunk = t & 7;                   // 16-byte chunk of the 128-byte row
         const int r0 = t >> 3;                     // rows r0 + 16*i, i = 0..7  (row & 7 == r0 & 7 for all of them)
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         // ---- LOAD cursor: (tile iteration, k-block in tile) of the next k-block this group loads; this lane's channel
         //      quad of that k-block is g = 8 kb + chunk -> (tap, quad in tap) by multiply-shift division
         int oy[8], ox[8], rowoff[8];
-        int l_ti = 0, l_kb = grp, cur_ti = -1;
+        int l_ti = 0, l_kb = grp, cur_ti = -1;      // (KB may be smaller than G)
         while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         auto set_tile = [&](int ti) {
             cur_ti = ti;
@@ -607,7 +612,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                 }
             }
             mask = mk;
-            l_kb += 2;
+            l_kb += G;
             while (l_kb >= KB) { l_kb -= KB; ++l_ti; }
         };
         // ---- store phase: wait for the stage, pre-op + hi/lo split in registers, swizzled 128-bit stores, publish.
@@ -615,13 +620,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         //      exact in fp32 and the tensor core reads its top 19 bits (error <= 2^-21 |x|).
         int s_s = grp;                             // stage of this group's next store (S >= 2)
         uint32_t s_ph = 0;
+        while (s_s >= S) { s_s -= S; s_ph ^= 1; }
         auto store_kb = [&](F4(&v)[8], uint32_t mask, const int c) {
             const uint32_t a_hi = base + (uint32_t)s_s * stage_bytes + roff0;
             const uint32_t a_lo = a_hi + A_TILE_BYTES;
             const uint32_t bar_full = full_a(s_s);
             mbar_wait(empty(s_s), s_ph ^ 1);
-            s_s += 2;
-            if (s_s >= S) { s_s -= S; s_ph ^= 1; }
+            s_s += G;
+            while (s_s >= S) { s_s -= S; s_ph ^= 1; }
             float sc[4], sh[4];
             if (AFF) {
                 const float4 a4 = *reinterpret_cast<const float4 *>(s_scale + c);
@@ -668,11 +674,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
         };
         // ---- software pipeline (register ping-pong): the loads of this group's next k-block -- possibly of the next
         //      tile -- are in flight while the current one is transformed and stored
-        {
+        const int mine = total_kb > grp ? (total_kb - grp + G - 1) / G : 0;   // k-blocks of this group
+        if constexpr (G == 2) {
             F4 va[8], vb[8];
             uint32_t ma = 0, mb = 0;
             int ca = 0, cb = 0;
-            const int mine = (total_kb - grp + 1) >> 1;   // k-blocks of this group
             int issued = 0;
             if (issued < mine) { load_kb(va, ma, ca); ++issued; }
             for (int done = 0; done < mine; done += 2) {
@@ -683,10 +689,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const ConvParam
                     store_kb(vb, mb, cb);
                 }
             }
+        } else {
+            F4 va[8];
+            uint32_t ma = 0;
+            int ca = 0;
+            for (int done = 0; done < mine; ++done) {
+                load_kb(va, ma, ca);
+                store_kb(va, ma, ca);
+            }
         }
         }   // !TMA
     } else {
-        // ===================== epilogue warps (10..13) =====================
+        // ===================== epilogue warps (the last four) =====================
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0);
@@ -925,6 +939,7 @@ extern "C" int bts_conv_pack_weights_grouped(const float *w, long long s_co, lon
 //      entry-point query: no link-time dependency on libcuda)
 static int g_issue_legacy = 0;  // 1: round-1 MMA issue loops in conv_tc / wgrad_tc / wgrad2_tc (fallback switch)
 int bts_issue_legacy() { return g_issue_legacy; }
+static int g_producer_groups = 0;   // 0 / 4: four groups where the ring has >= 4 stages, 2: always two
 static int g_tma_mode = 0;      // 0 off, 1 on, 2 on with base-pixel coordinates NOT shifted by the lower corner, 3 on + strict
 
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -968,6 +983,11 @@ extern "C" int bts_conv_set_tma(int mode) {
     return 0;
 }
 extern "C" int bts_conv_get_tma(void) { return g_tma_mode; }
+extern "C" int bts_conv_set_producer_groups(int g) {
+    if (g != 0 && g != 2 && g != 4) return BTS_EINVAL;
+    g_producer_groups = g;
+    return 0;
+}
 
 // 1 (default): lean whole-warp MMA issue loops; 0: the round-1 single-lane loops (kept as a fallback switch for bring-up)
 extern "C" int bts_conv_set_issue_mode(int lean) {
@@ -1071,17 +1091,26 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
             return rc;                                   // forced: report why the map could not be built
         }
     }
-#define BTS_LAUNCH(PRE, UP, VEC, TMA)                                                                              \
+    // four producer groups wherever the ring has >= 4 stages for them to work concurrently (i.e. every layer but the
+    // 256-wide tiles, which are tensor-bound anyway).  Measured on B200 (profiles/r02_producer_groups.txt): dense 3x3
+    // 192->48 457 -> 393 us, 161->64 1.38 -> 1.22 ms, never slower; K16 step 99.4 -> 97.4 ms.
+    const bool four = !use_tma && !g_issue_legacy && p.stages >= 4 && g_producer_groups != 2;
+#define BTS_LAUNCH_G(PRE, UP, VEC, TMA, G)                                                                         \
     do {                                                                                                           \
         static bool attr_set_[BTS_MAX_DEVICES] = {};                                                               \
         bool &attr_set = attr_set_[bts_cur_device()];                                                              \
         if (!attr_set) {                                                                                           \
-            err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            err = cudaFuncSetAttribute(conv_tc_kernel<PRE, UP, VEC, TMA, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        SMEM_LIMIT);                                                                \
             if (err != cudaSuccess) return (int)err;                                                               \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        conv_tc_kernel<PRE, UP, VEC, TMA><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p, tmap);             \
+        conv_tc_kernel<PRE, UP, VEC, TMA, G><<<grid, 192 + 128 * G, smem, (cudaStream_t)stream>>>(p, tmap);         \
+    } while (0)
+#define BTS_LAUNCH(PRE, UP, VEC, TMA)                                                                              \
+    do {                                                                                                           \
+        if (four && VEC && !TMA) BTS_LAUNCH_G(PRE, UP, true, false, 4);                                            \
+        else BTS_LAUNCH_G(PRE, UP, VEC, TMA, 2);                                                                   \
     } while (0)
 #define BTS_DISPATCH_UV(PRE)                                  \
     do {                                                      \
@@ -1098,6 +1127,7 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     }
 #undef BTS_DISPATCH_UV
 #undef BTS_LAUNCH
+#undef BTS_LAUNCH_G
     BTS_LAUNCH_CHECK();
     return 0;
 }

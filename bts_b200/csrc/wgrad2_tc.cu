@@ -266,11 +266,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         }
         constexpr int NBU = 6;                     // dY units per thread per k-block: <= 3 taps x 2 chunks
         constexpr int NAU = 1;                     // x units per thread per k-block
-        // tap offsets of this thread's taps (t = half, half+4, half+8), computed once: no divisions in the k-loop
+        // Unit slots (j, ch), j = 0..2, ch = 0..1.  Multi-tap layers: tap t = half + 4j, 32-channel chunk ch of <= 2.
+        // Single-tap (1x1) layers: tap 0, chunk half + 4*(2j + ch) of <= 8 (an output tile up to 256 channels wide).
+        const bool single = taps == 1;
+        auto unit_tap = [&](int j) { return single ? 0 : half + 4 * j; };
+        auto unit_chunk = [&](int j, int ch) { return single ? half + 4 * (2 * j + ch) : ch; };
+        // tap offsets of this thread's taps, computed once: no divisions in the k-loop
         int toy[NBU / 2], tox[NBU / 2], tky[NBU / 2];
 #pragma unroll
         for (int j = 0; j < NBU / 2; ++j) {
-            const int t = half + 4 * j;
+            const int t = unit_tap(j);
             const int ky = t / p.KW, kx = t - ky * p.KW;
             toy[j] = ky * p.dil - p.pad;
             tox[j] = kx * p.dil - p.pad;
@@ -283,10 +288,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         for (int j = 0; j < NBU / 2; ++j)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                const int t = half + 4 * j;
-                const int c = unit * 4 + ch * 32;                         // channel within this CTA's group
+                const int t = unit_tap(j), cc = unit_chunk(j, ch);
+                const int c = unit * 4 + cc * 32;                         // channel within this CTA's group
                 const int n = t * ncol + c;
-                blive[j * 2 + ch] = t < taps && ch < nb && c < ncol;
+                blive[j * 2 + ch] = t < taps && cc < nb && c < ncol;
                 boff[j * 2 + ch] = (uint32_t)(n >> 5) * CHUNK + mn_swizzle_off(row, (n & 31) >> 2);
             }
         struct Cursor { int qx, qy, qb; };
@@ -331,14 +336,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         auto load_d = [&](const Cursor &c_, bool okx, F4(&vb)[NBU]) {
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
-                const int t = half + 4 * j;
+                const int t = unit_tap(j);
                 const int py = c_.qy - toy[j], px = c_.qx - tox[j];
                 const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
                 const int doff = ((c_.qb * p.Hout + py) * p.Wout + px) * dys;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
-                    const int c = cbd + ch * 32;
-                    const bool live = okd && ch < nb && c < p.Cout && (c - co0) < ncol;
+                    const int c = cbd + unit_chunk(j, ch) * 32;
+                    const bool live = okd && blive[j * 2 + ch] && c < p.Cout;
                     F4 &dst = vb[j * 2 + ch];
                     if (VEC) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
             }
 #pragma unroll
             for (int j = 0; j < NBU / 2; ++j) {
-                const int t = half + 4 * j;
+                const int t = unit_tap(j);
                 const int py = cur.qy - toy[j], px = cur.qx - tox[j];
                 const bool okd = okx && t < taps && (unsigned)py < (unsigned)p.Hout && (unsigned)px < (unsigned)p.Wout;
                 const uint32_t rowb = segb + (uint32_t)tky[j] * (uint32_t)p.seg_bytes +
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
                 for (int ch = 0; ch < 2; ++ch) {
                     F4 &dst = vb[j * 2 + ch];
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (okd && blive[j * 2 + ch]) v = ld_shared_v4(rowb + (uint32_t)ch * 128u);
+                    if (okd && blive[j * 2 + ch]) v = ld_shared_v4(rowb + (uint32_t)unit_chunk(j, ch) * 128u);
                     dst.v[0] = v.x; dst.v[1] = v.y; dst.v[2] = v.z; dst.v[3] = v.w;
                 }
             }
@@ -485,9 +490,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad2_tc_kernel(const W2Param
         const int q4 = warp & 3;
         const int ci = ci_tile * BLOCK_CI + q4 * 32 + lane;
         const bool ovec = (p.Cout & 3) == 0 && ((((uintptr_t)p.part) & 15) == 0) && ((co0 & 3) == 0);
-        for (int t = half; t < taps; t += 4) {
+        // multi-tap: the taps are split between the four quarters; single-tap: the 8-column blocks of the one tap are
+        for (int t = single ? 0 : half; t < taps; t += single ? 1 : 4) {
             float *prow = p.part + (((long long)split * taps + t) * p.Cin + (ci < p.Cin ? ci : 0)) * p.Cout + co0;
-            for (int cc = 0; cc < ncol; cc += 8) {
+            for (int cc = single ? half * 8 : 0; cc < ncol; cc += single ? 32 : 8) {
                 uint32_t r[8];
                 tmem_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(t * ncol + cc), r);
                 tmem_ld_wait();
@@ -521,7 +527,11 @@ int bts_issue_legacy();
 // co-group width for the shifted-dY kernel: multiple of 16, taps*cg <= 512 TMEM columns, groups as even as possible
 int bts_wgrad2_cg(int Cout, int taps) {
     int cap = (512 / taps) / 16 * 16;
-    if (cap > 48) cap = 48;
+    if (taps == 1) {
+        if (cap > 256) cap = 256;              // 1x1: one tile up to 256 output channels wide (one tcgen05.mma)
+    } else if (cap > 48) {
+        cap = 48;
+    }
     if (cap < 16) return 0;
     const int groups = (Cout + cap - 1) / cap;
     int cg = ((Cout + groups - 1) / groups + 15) / 16 * 16;
@@ -529,14 +539,21 @@ int bts_wgrad2_cg(int Cout, int taps) {
     return cg;
 }
 
-// measured (B200, K16 shapes): wins for Cout <= 48 on maps of >= 60k pixels (dense 3x3 of blocks 1-2, conv1, upconv1);
-// loses for Cout = 64 (two co groups re-produce the activation tile) and on the small maps of blocks 3-4
-static long long g_w2_min_pixels = 60000;
-extern "C" int bts_wgrad2_set_min_pixels(long long n) { g_w2_min_pixels = n < 0 ? 60000 : n; return 0; }
+// measured (B200, K16 shapes, profiles/r02_w2_sweep.txt): with the TMA landing ring it beats the tap-in-grid kernel on
+// every narrow-output 3x3 layer down to the 22x44 maps of block 3 (40 vs 71 us with >= 8 k-blocks per split-K CTA and one
+// wave of CTAs); on the 11x22 maps of block 4 (3.9k pixels) the two tie and the tap-in-grid kernel stays
+static long long g_w2_min_pixels = 12000;
+static int g_w2_pointwise = 1;               // 1x1 layers (64 < Cout <= 256) on this kernel too
+extern "C" int bts_wgrad2_set_pointwise(int on) { g_w2_pointwise = on ? 1 : 0; return 0; }
+static int g_w2_min_kb = 8;                  // fewest 16-pixel k-blocks a split-K CTA gets
+extern "C" int bts_wgrad2_set_min_pixels(long long n) { g_w2_min_pixels = n < 0 ? 12000 : n; return 0; }
+extern "C" int bts_wgrad2_set_min_kblocks(int n) { g_w2_min_kb = n < 1 ? 8 : n; return 0; }
 
 bool bts_wgrad2_eligible(int Cout, int KH, int KW, int stride, long long Mq) {
     const int taps = KH * KW;
-    return taps > 1 && taps <= MAX_TAPS && Cout <= 64 && stride == 1 && Mq >= g_w2_min_pixels && bts_wgrad2_cg(Cout, taps) > 0;
+    if (stride != 1 || Mq < g_w2_min_pixels || taps > MAX_TAPS || bts_wgrad2_cg(Cout, taps) <= 0) return false;
+    if (taps == 1) return g_w2_pointwise && Cout > 64 && Cout <= 256;   // 1x1 layers with one <= 256-wide output tile
+    return Cout <= 64;
 }
 
 void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW, int *splitK) {
@@ -546,7 +563,7 @@ void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW,
     const long long KBq = (Mq + KP - 1) / KP;
     const long long tiles = (long long)((Cin + BLOCK_CI - 1) / BLOCK_CI) * ((Cout + cg - 1) / cg);
     const int sms = bts_num_sms();
-    long long max_split = (KBq + 31) / 32;
+    long long max_split = (KBq + g_w2_min_kb - 1) / g_w2_min_kb;
     if (max_split < 1) max_split = 1;
     if (max_split > 512) max_split = 512;
     long long split = 1;
@@ -556,7 +573,7 @@ void bts_wgrad2_plan(int B, int Hin, int Win, int Cin, int Cout, int KH, int KW,
         const long long waves = (ctas + sms - 1) / sms;
         if (waves > 2 && sp > 1) break;
         const double eff = (double)ctas / (double)(waves * sms);
-        if (eff >= best - 1e-9) { best = eff; split = sp; }
+        if (eff > best + 1e-9) { best = eff; split = sp; }      // ties -> fewer splits: less partial traffic for the reduce
     }
     *splitK = (int)split;
 }

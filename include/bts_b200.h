@@ -144,11 +144,16 @@ int bts_conv_get_tma(void);
 /* MMA issue loops of the three tensor-core kernels: 1 (default) = whole-warp loop with one elected lane, one barrier per stage,
  * incrementally advanced descriptors; 0 = the round-1 single-lane loops, kept as a bring-up fallback.  Process-wide. */
 int bts_conv_set_issue_mode(int lean);
+/* activation-producer groups of the conv engine (4 warps each): 0 / 4 = four groups without register prefetch wherever the
+ * operand ring has >= 4 stages (default), 2 = always two groups with one k-block of register prefetch (round-1 layout). */
+int bts_conv_set_producer_groups(int groups);
 /* Tuning / bring-up switches of the narrow-output wgrad (csrc/wgrad2_tc.cu).  set_tma(0): the producers load the operands
  * from global memory (round-1 path) instead of the TMA landing ring; set_min_pixels(n): smallest map (input pixels) routed to
- * this kernel (default 60000, n < 0 restores it; tests pass 0 to reach it with small shapes). */
+ * this kernel (default 12000, n < 0 restores it; tests pass 0 to reach it with small shapes). */
 int bts_wgrad2_set_tma(int on);
 int bts_wgrad2_set_min_pixels(long long n);
+int bts_wgrad2_set_min_kblocks(int n);
+int bts_wgrad2_set_pointwise(int on);        /* 1 (default): 1x1 layers with 64 < Cout <= 256 use this kernel too */       /* fewest 16-pixel k-blocks per split-K CTA (default 8; n < 1 restores) */
 
 /* dgrad (or any act-free conv) whose epilogue also reduces the BatchNorm(+ReLU)-backward sums of the layer in front of the
  * conv: the tile written is g = dL/d[relu](bn(x_bn)); S1[c] += sum_p g*mask, S2[c] += sum_p g*mask*xhat (zero them first),

@@ -140,7 +140,7 @@ def test_single_output_channel_head_kernels(C, K, sig):
 
 @pytest.fixture(params=["tma_ring", "global_loads", "auto_small_map"])
 def w2_mode(request):
-    """routes small test shapes to the shifted-dY kernel (its production threshold is 60k pixels) with the operands staged
+    """routes small test shapes to the shifted-dY kernel (its production threshold is 12k pixels) with the operands staged
     through the TMA landing ring or loaded by the producers; 'auto_small_map' leaves the production routing (wgrad_tc)"""
     from bts_b200 import _lib
     L = _lib.lib()
@@ -181,6 +181,28 @@ def test_wgrad_narrow_output_shifted_dy_kernel(w2_mode, Cin, Cout, H, W, dil, up
                        pre_scale=sc.cuda() if pre else None, pre_shift=sh.cuda() if pre else None, pre_relu=pre,
                        upsample2=up)
     err = (gw.cpu().double() - wd.grad).abs().max() / wd.grad.abs().max()
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W,pre", [(240, 192, 9, 14, True), (96, 128, 16, 16, False), (300, 192, 7, 9, True),
+                                               (64, 256, 8, 8, False), (130, 80, 5, 7, True), (2064, 192, 6, 11, True)])
+def test_wgrad_pointwise_wide_tile_on_shifted_dy_kernel(w2_mode, Cin, Cout, H, W, pre):
+    """1x1 layers with 64 < Cout <= 256 (dense-layer conv1, transitions, decoder reductions): one <= 256-wide output tile per
+    CTA on wgrad2_tc.cu (single-tap unit mapping), TMA ring / global loads / production routing -- vs torch fp64."""
+    from bts_b200 import conv
+    g = torch.Generator().manual_seed(Cin * 7 + Cout)
+    x = torch.randn(3, Cin, H, W, generator=g)
+    gy = torch.randn(3, Cout, H, W, generator=g)
+    sc = torch.rand(Cin, generator=g) + 0.5
+    sh = torch.randn(Cin, generator=g) * 0.3
+    xd = x.double()
+    if pre:
+        xd = F.relu(xd * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1))
+    ref = torch.einsum("bohw,bihw->oi", gy.double(), xd).reshape(Cout, Cin, 1, 1)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    gw = conv.wgrad_tc(xc, gy.cuda().contiguous(memory_format=torch.channels_last), (Cout, Cin, 1, 1), (Cin, 1, 1, 1), 1, 0, 1,
+                       pre_scale=sc.cuda() if pre else None, pre_shift=sh.cuda() if pre else None, pre_relu=pre)
+    err = (gw.cpu().double() - ref).abs().max() / ref.abs().max()
     assert err < 2e-5, err
 
 
