@@ -841,13 +841,19 @@ def _run_ours(args):
                     if "conv" in rl:
                         res["roofline"] = dict(rl["conv"], kernel="conv_tc_kernel (tcgen05 implicit GEMM: every conv forward and "
                                                                   "dgrad of the step), all launches of one real training step",
-                                               # ncu --set full, profiles/r01_conv5_v4.ncu-rep: conv5 896->512 @22x44x16, one launch:
-                                               # 115.0 MB read + 10.7 MB written vs 88 MB algorithmic (input 55.5 + output 31.7 + weights)
-                                               traffic=125.7e6, traffic_unit="bytes, ONE launch of the conv5 layer (ncu capture "
-                                                                             "profiles/r01_conv5_v4.ncu-rep; algorithmic 88 MB)")
+                                               # ncu --set full, profiles/r02_conv_db1_final.ncu-rep: dense 3x3 192->48 @88x176x16
+                                               # (the most frequent shape of the kernel), one launch: 191.1 MB read + 33.8 MB
+                                               # written vs 238.0 MB algorithmic (input 190.3 + output 47.6 + weights 0.08)
+                                               traffic=224.9e6, traffic_unit="bytes, ONE launch of the dense 3x3 192->48 layer (ncu "
+                                                                             "capture profiles/r02_conv_db1_final.ncu-rep; algorithmic "
+                                                                             "238 MB: no re-reads from DRAM; l1tex 82 %, tensor pipe 33 %)")
                     if "wgrad" in rl:
                         res["roofline_wgrad"] = dict(rl["wgrad"], kernel="wgrad kernels (tcgen05, MN-major operands), all launches "
-                                                                         "of one real training step", traffic=None)
+                                                                         "of one real training step",
+                                                     # profiles/r02_wgrad2_db1_final.ncu-rep (dense 3x3 wgrad): 243.0 MB read + 3.8 MB written
+                                                     # vs 238.0 MB algorithmic (x 190.3 + dY 47.6); tensor pipe 72.6 %
+                                                     traffic=246.8e6, traffic_unit="bytes, ONE launch of the dense 3x3 192->48 wgrad (ncu, "
+                                                                                   "profiles/r02_wgrad2_db1_final.ncu-rep; algorithmic 238 MB)")
                 except Exception as e:
                     res["roofline"] = {"error": "%s: %s" % (type(e).__name__, e)}
             del model, opt

@@ -187,6 +187,195 @@ __global__ void __launch_bounds__(256) thin_wgrad(const ThinParams p) {
     }
 }
 
+// ---- 3x3 variants with vertical register reuse (round 2).  The per-pixel kernels above issue 9 sixteen-byte loads, 64-bit
+// index arithmetic and a bounds test per tap and pixel; at 352x704x32 that, not HBM, set the time (0.83 / 0.67 / 0.85 ms
+// per K16 step against ~0.1 ms of traffic).  Here a lane group owns a COLUMN RUN of R pixels: the 3 x (R+2) input window
+// is loaded once (2.4x fewer loads for R = 8), row validity is warp-uniform, the weights of the lane's 4 channels sit in
+// registers, and R accumulators give the FMA pipe independent chains.
+constexpr int RUN = 8;
+
+struct RunIndex { int x, y0, b; bool live; };
+
+template <int LPP>
+__device__ __forceinline__ RunIndex run_index(const ThinParams &p, long long work, int slot) {
+    constexpr int PPW = 32 / LPP;
+    const int xgroups = (p.W + PPW - 1) / PPW, strips = (p.H + RUN - 1) / RUN;
+    RunIndex r;
+    const int xg = (int)(work % xgroups);
+    const long long t = work / xgroups;
+    r.x = xg * PPW + slot;
+    r.y0 = (int)(t % strips) * RUN;
+    r.b = (int)(t / strips);
+    r.live = r.x < p.W;
+    return r;
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256) thin_fwd3(const ThinParams p) {
+    __shared__ __align__(16) float sw[MAXTAPS * MAXC];
+    load_w(p, sw);
+    const int lane = threadIdx.x & 31;
+    const int u = lane % LPP, slot = lane / LPP;
+    constexpr int PPW = 32 / LPP;
+    float4 w[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4 *>(sw + t * p.C + 4 * u);
+    const long long nwork = (long long)p.B * ((p.H + RUN - 1) / RUN) * ((p.W + PPW - 1) / PPW);
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long work = warp0; work < nwork; work += nwarps) {
+        const RunIndex ri = run_index<LPP>(p, work, slot);
+        float acc[RUN];
+#pragma unroll
+        for (int r = 0; r < RUN; ++r) acc[r] = 0.f;
+        const float *base = p.x + ((long long)ri.b * p.H * p.W) * p.xs + 4 * u;
+#pragma unroll
+        for (int r = -1; r <= RUN; ++r) {                       // input row y0 + r feeds output rows r - ky + 1
+            const int yy = ri.y0 + r;
+            if ((unsigned)yy >= (unsigned)p.H) continue;        // warp-uniform
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = ri.x + kx - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ri.live && (unsigned)xx < (unsigned)p.W)
+                    v = __ldg(reinterpret_cast<const float4 *>(base + ((long long)yy * p.W + xx) * p.xs));
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int ro = r - ky + 1;
+                    if (ro >= 0 && ro < RUN) {
+                        const float4 wv = w[ky * 3 + kx];
+                        float a = acc[ro];
+                        a = fmaf(v.x, wv.x, a); a = fmaf(v.y, wv.y, a); a = fmaf(v.z, wv.z, a); a = fmaf(v.w, wv.w, a);
+                        acc[ro] = a;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RUN; ++r) {
+            float a = acc[r];
+#pragma unroll
+            for (int m = 1; m < LPP; m <<= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+            if (u == 0 && ri.live && ri.y0 + r < p.H) {
+                if (p.act == 2) a = 1.0f / (1.0f + expf(-a));
+                p.y[((long long)ri.b * p.H + ri.y0 + r) * p.W + ri.x] = a;
+            }
+        }
+    }
+}
+
+// the 3 x (RUN+2) window of effective upstream gradients around a column run: win[r + 1][kx] = g(y0 + r, x + kx - 1)
+template <int LPP>
+__device__ __forceinline__ void load_gwin(const ThinParams &p, const RunIndex &ri, float (&win)[RUN + 2][3]) {
+#pragma unroll
+    for (int r = -1; r <= RUN; ++r) {
+        const int yy = ri.y0 + r;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = ri.x + kx - 1;
+            float gv = 0.f;
+            if (ri.live && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W)
+                gv = geff(p, (size_t)(((long long)ri.b * p.H + yy) * p.W + xx));
+            win[r + 1][kx] = gv;
+        }
+    }
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256) thin_dgrad3(const ThinParams p) {
+    __shared__ __align__(16) float sw[MAXTAPS * MAXC];
+    load_w(p, sw);
+    const int lane = threadIdx.x & 31;
+    const int u = lane % LPP, slot = lane / LPP;
+    constexpr int PPW = 32 / LPP;
+    float4 w[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t] = *reinterpret_cast<const float4 *>(sw + t * p.C + 4 * u);
+    const long long nwork = (long long)p.B * ((p.H + RUN - 1) / RUN) * ((p.W + PPW - 1) / PPW);
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long work = warp0; work < nwork; work += nwarps) {
+        const RunIndex ri = run_index<LPP>(p, work, slot);
+        float win[RUN + 2][3];
+        load_gwin<LPP>(p, ri, win);
+#pragma unroll
+        for (int r = 0; r < RUN; ++r) {
+            // dx[y][x] = sum_tap g[y - (ky - 1)][x - (kx - 1)] * w[tap]
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float gv = win[r - (ky - 1) + 1][2 - kx];
+                    const float4 wv = w[ky * 3 + kx];
+                    acc.x = fmaf(gv, wv.x, acc.x); acc.y = fmaf(gv, wv.y, acc.y);
+                    acc.z = fmaf(gv, wv.z, acc.z); acc.w = fmaf(gv, wv.w, acc.w);
+                }
+            if (ri.live && ri.y0 + r < p.H)
+                *(reinterpret_cast<float4 *>(p.dx + (((long long)ri.b * p.H + ri.y0 + r) * p.W + ri.x) * p.dxs) + u) = acc;
+        }
+    }
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256) thin_wgrad3(const ThinParams p) {
+    constexpr int TAPS = 9;
+    constexpr int PPW = 32 / LPP;
+    __shared__ float red[8][TAPS * 4 * LPP];            // per-warp results: [tap][channel]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = lane % LPP, slot = lane / LPP;
+    const long long nwork = (long long)p.B * ((p.H + RUN - 1) / RUN) * ((p.W + PPW - 1) / PPW);
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float4 acc[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long work = warp0; work < nwork; work += nwarps) {
+        const RunIndex ri = run_index<LPP>(p, work, slot);
+        float win[RUN + 2][3];
+        load_gwin<LPP>(p, ri, win);
+        const float *base = p.x + ((long long)ri.b * p.H * p.W) * p.xs + 4 * u;
+#pragma unroll
+        for (int r = 0; r < RUN; ++r) {
+            // dw[tap] += x[q] * g[q - off(tap)],  q = (y0 + r, x): each input pixel is read once
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ri.live && ri.y0 + r < p.H)
+                v = __ldg(reinterpret_cast<const float4 *>(base + ((long long)(ri.y0 + r) * p.W + ri.x) * p.xs));
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float gv = win[r - (ky - 1) + 1][2 - kx];
+                    float4 &a = acc[ky * 3 + kx];
+                    a.x = fmaf(gv, v.x, a.x); a.y = fmaf(gv, v.y, a.y);
+                    a.z = fmaf(gv, v.z, a.z); a.w = fmaf(gv, v.w, a.w);
+                }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+#pragma unroll
+        for (int m = LPP; m < 32; m <<= 1) {
+            acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, m);
+            acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, m);
+            acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, m);
+            acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, m);
+        }
+        if (slot == 0) {
+            float *r = &red[warp][t * 4 * LPP + 4 * u];
+            r[0] = acc[t].x; r[1] = acc[t].y; r[2] = acc[t].z; r[3] = acc[t].w;
+        }
+    }
+    __syncthreads();
+    const int n = TAPS * 4 * LPP;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) sum += red[wv][i];
+        p.part[(size_t)blockIdx.x * n + i] = sum;
+    }
+}
+
 __global__ void thin_wgrad_reduce(const float *__restrict__ part, int nblocks, int C, int K, float *__restrict__ dw,
                                   long long s_ci, long long s_kh, long long s_kw) {
     const int n = K * K * C;
@@ -203,6 +392,16 @@ int lpp_of(int C) { return (C == 8 || C == 16 || C == 32 || C == 64 || C == 128)
 int grid_for(long long npix, int lpp) {
     const long long groups = (npix + (32 / lpp) - 1) / (32 / lpp);
     long long blocks = (groups + 7) / 8;
+    const long long cap = (long long)bts_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int grid_for_runs(int B, int H, int W, int lpp) {
+    const int ppw = 32 / lpp;
+    const long long work = (long long)B * ((H + RUN - 1) / RUN) * ((W + ppw - 1) / ppw);
+    long long blocks = (work + 7) / 8;
     const long long cap = (long long)bts_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -238,8 +437,14 @@ extern "C" int bts_conv_c1_fwd(const float *x, long long x_pixel_stride, int B, 
     ThinParams p{};
     p.x = x; p.xs = x_pixel_stride; p.B = B; p.H = H; p.W = W; p.C = C; p.K = K;
     p.w = w; p.s_ci = s_ci; p.s_kh = s_kh; p.s_kw = s_kw; p.y = y; p.act = act;
-    const int grid = grid_for((long long)B * H * W, lpp_of(C));
     cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && C <= 64 && H >= RUN) {
+        const int grid3 = grid_for_runs(B, H, W, lpp_of(C));
+        BTS_THIN_DISPATCH(thin_fwd3, <<<grid3, 256, 0, st>>>(p))
+        BTS_LAUNCH_CHECK();
+        return 0;
+    }
+    const int grid = grid_for((long long)B * H * W, lpp_of(C));
     BTS_THIN_DISPATCH(thin_fwd, <<<grid, 256, 0, st>>>(p))
     BTS_LAUNCH_CHECK();
     return 0;
@@ -254,8 +459,14 @@ extern "C" int bts_conv_c1_dgrad(const float *dy, const float *sig, int B, int H
     ThinParams p{};
     p.B = B; p.H = H; p.W = W; p.C = C; p.K = K; p.w = w; p.s_ci = s_ci; p.s_kh = s_kh; p.s_kw = s_kw;
     p.dy = dy; p.s = sig; p.dx = dx; p.dxs = dx_pixel_stride;
-    const int grid = grid_for((long long)B * H * W, lpp_of(C));
     cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && C <= 64 && H >= RUN) {
+        const int grid3 = grid_for_runs(B, H, W, lpp_of(C));
+        BTS_THIN_DISPATCH(thin_dgrad3, <<<grid3, 256, 0, st>>>(p))
+        BTS_LAUNCH_CHECK();
+        return 0;
+    }
+    const int grid = grid_for((long long)B * H * W, lpp_of(C));
     BTS_THIN_DISPATCH(thin_dgrad, <<<grid, 256, 0, st>>>(p))
     BTS_LAUNCH_CHECK();
     return 0;
@@ -270,11 +481,13 @@ extern "C" int bts_conv_c1_wgrad(const float *x, long long x_pixel_stride, const
     ThinParams p{};
     p.x = x; p.xs = x_pixel_stride; p.B = B; p.H = H; p.W = W; p.C = C; p.K = K;
     p.dy = dy; p.s = sig; p.part = workspace;
-    const int grid = grid_for((long long)B * H * W, lpp_of(C));
-    cudaStream_t st = (cudaStream_t)stream;
     const int lpp = lpp_of(C);
+    const bool runs = K == 3 && C <= 64 && H >= RUN;
+    const int grid = runs ? grid_for_runs(B, H, W, lpp) : grid_for((long long)B * H * W, lpp);
+    cudaStream_t st = (cudaStream_t)stream;
 #define BTS_WG(L)                                                             \
     if (K == 1) thin_wgrad<L, 1><<<grid, 256, 0, st>>>(p);                    \
+    else if (runs) thin_wgrad3<L><<<grid, 256, 0, st>>>(p);                   \
     else thin_wgrad<L, 3><<<grid, 256, 0, st>>>(p);
     switch (lpp) {
         case 2: BTS_WG(2) break;

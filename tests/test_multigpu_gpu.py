@@ -18,4 +18,6 @@ def test_ddp_gradients_are_shard_means_and_buffers_follow_rank0(enc):
            "--master-port", "29517", os.path.join(ROOT, "tests", "dist_worker.py"), enc]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT,
                        env=dict(os.environ, BTS_B200_PRETRAINED="0"))
-    assert r.returncode == 0 and "DIST_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+    if r.returncode != 0 or "DIST_OK" not in r.stdout:
+        sys.stderr.write("---- worker stdout ----\n" + r.stdout[-6000:] + "\n---- worker stderr ----\n" + r.stderr[-12000:] + "\n")
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, "worker failed (see captured stderr)"
