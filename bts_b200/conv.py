@@ -16,6 +16,7 @@ from .ops import _need_cuda, _ptr, _stream
 ACT = {None: 0, "none": 0, "elu": 1, "sigmoid": 2}
 import os as _os
 
+PW_FWD = _os.environ.get("BTS_B200_PW_FWD", "1") == "1"      # CUDA-core forward / dgrad for the same layers
 PW_WGRAD = True                                               # CUDA-core wgrad for narrow 1x1 layers (csrc/pointwise.cu)
 PW_MIN_PIXELS = 200000                                        # below this the tensor-core path is already short
 TRACE = _os.environ.get("BTS_B200_TRACE", "0") == "1"     # per-call CUDA-event timing, aggregated by shape
@@ -226,6 +227,30 @@ def conv2d_tc(x, weight, stride=1, padding=0, dilation=1, pre_scale=None, pre_sh
         Co, Ci = Ci, Co
     if Ci != Cin:
         raise ValueError("weight expects %d input channels, got %d" % (Ci, Cin))
+    if (PW_FWD and KH == 1 and KW == 1 and stride == 1 and padding == 0 and groups == 1 and not upsample2
+            and zero_stuff_out is None and pre_scale is None and not pre_relu and stats is None and bn_bwd is None
+            and precision == 0 and packed is None and act in ACT and B * Hs * Ws >= PW_MIN_PIXELS
+            and xs % 4 == 0 and x.data_ptr() % 16 == 0 and _lib.lib().bts_conv_pw_fwd_eligible(Cin, Co)):
+        # narrow 1x1 layers of the reduction heads (forward and dgrad): HBM-bound CUDA-core kernel (csrc/pointwise.cu)
+        if out is None:
+            out = torch.empty((B, Co, Hs, Ws), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+            os_ = Co
+        else:
+            if tuple(out.shape) != (B, Co, Hs, Ws):
+                raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), (B, Co, Hs, Ws)))
+            o2, os_ = _nhwc_view(out)
+            if o2 is not out:
+                raise ValueError("out must be NHWC in memory")
+        ws = weight.stride()
+        s_out, s_in = (ws[1], ws[0]) if transpose_flip else (ws[0], ws[1])
+        with torch.cuda.device(x.device):
+            rc = _traced("pwdgrad" if transpose_flip else "pwfwd", "%dx%dx%d %d->%d k1" % (B, Hs, Ws, Cin, Co),
+                         lambda: _lib.lib().bts_conv_pw_fwd(_ptr(x), xs, B * Hs * Ws, Cin, _ptr(weight), s_out, s_in, Co,
+                                                            ACT[act], _ptr(out), os_, _stream()),
+                         2.0 * B * Hs * Ws * Co * Cin)
+        _lib.check(rc, "bts_conv_pw_fwd")
+        _lib.count()
+        return out
     flags = pack_flags(weight.shape, transpose_flip, groups)
     if upsample2 or zero_stuff_out is not None:
         flags &= ~1                          # the up-sampled / zero-stuffed address maps keep the dense tap-major K order

@@ -147,3 +147,106 @@ extern "C" int bts_conv_pw_wgrad(const float *x, long long x_pixel_stride, const
     BTS_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forward / dgrad of the same narrow 1x1 layers (round 2).  On the tensor engine they ran at 2-16 TF/s -- 0.54 ms for
+// 32->16 at 352x704x16 against 0.12 ms of HBM time (profiles/r02_step_trace_*.txt): a 128x16 output tile leaves the MMA
+// at its 45-cycle floor while the full operand-staging pipeline still runs.  Here:
+//   out[p, co] = act( sum_ci x[p, ci] * W[co, ci] )        dgrad: the same with W read transposed (x := dY)
+// A thread owns one pixel and one group of 4 output channels (the groups of a pixel are adjacent lanes, so the x row of a
+// pixel is a broadcast load and a warp writes 512 contiguous bytes); x sits in registers, the (transposed, zero-padded)
+// weights in shared memory as float4 rows.  HBM-bound: 4*(Cin + Cout) bytes per pixel.
+namespace {
+
+constexpr int PWF_MAXCI = 64, PWF_MAXCO = 64;
+
+struct PwfParams {
+    const float *x; long long xs;
+    long long M;
+    const float *w; long long s_out, s_in;   // W[out, in] element strides (dgrad passes them swapped)
+    int Cout, act;                            // act: 0 none, 1 ELU, 2 sigmoid
+    float *out; long long os;
+    int ncog, lg;                             // output-channel groups of 4 (padded to a power of two = 1 << lg)
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(256) pw_fwd_kernel(const PwfParams p) {
+    __shared__ __align__(16) float sw[CIN * PWF_MAXCO];          // [ci][co padded to 4 << lg]
+    const int cop = 4 << p.lg;
+    for (int i = threadIdx.x; i < CIN * cop; i += blockDim.x) {
+        const int ci = i / cop, co = i - ci * cop;
+        sw[i] = co < p.Cout ? p.w[co * p.s_out + ci * p.s_in] : 0.f;
+    }
+    __syncthreads();
+    const int cog = (int)threadIdx.x & ((1 << p.lg) - 1);
+    const long long ppb = 256 >> p.lg;                            // pixels per block iteration
+    const bool ovec = ((p.os & 3) == 0) && ((((uintptr_t)p.out) & 15) == 0) && ((p.Cout & 3) == 0);
+    for (long long m = (long long)blockIdx.x * ppb + ((int)threadIdx.x >> p.lg); m < p.M; m += (long long)gridDim.x * ppb) {
+        float xv[CIN];
+        const float4 *xr = reinterpret_cast<const float4 *>(p.x + m * p.xs);
+#pragma unroll
+        for (int j = 0; j < CIN / 4; ++j) {
+            const float4 v = __ldg(xr + j);
+            xv[4 * j] = v.x; xv[4 * j + 1] = v.y; xv[4 * j + 2] = v.z; xv[4 * j + 3] = v.w;
+        }
+        if (cog >= p.ncog) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *wr = reinterpret_cast<const float4 *>(sw) + cog;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float4 wv = wr[ci << p.lg];
+            acc.x = fmaf(xv[ci], wv.x, acc.x); acc.y = fmaf(xv[ci], wv.y, acc.y);
+            acc.z = fmaf(xv[ci], wv.z, acc.z); acc.w = fmaf(xv[ci], wv.w, acc.w);
+        }
+        float r[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (p.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = r[e] > 0.f ? r[e] : expm1f(r[e]);
+        } else if (p.act == 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = 1.0f / (1.0f + expf(-r[e]));
+        }
+        float *o = p.out + m * p.os + cog * 4;
+        if (ovec) {
+            *reinterpret_cast<float4 *>(o) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (cog * 4 + e < p.Cout) o[e] = r[e];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int bts_conv_pw_fwd_eligible(int Cin, int Cout) {
+    return (Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && Cout >= 1 && Cout <= PWF_MAXCO;
+}
+
+// x: [M pixels][Cin] with pixel stride; w: element strides of W[out, in] (for dgrad pass the conv weight's (s_ci, s_co));
+// act: 0 none, 1 ELU, 2 sigmoid; out: [M][Cout] with pixel stride
+extern "C" int bts_conv_pw_fwd(const float *x, long long x_pixel_stride, long long M, int Cin, const float *w, long long s_out,
+                               long long s_in, int Cout, int act, float *out, long long out_pixel_stride, void *stream) {
+    if (!x || !w || !out || M < 1 || !bts_conv_pw_fwd_eligible(Cin, Cout) || act < 0 || act > 2) return BTS_EINVAL;
+    if (!bts_aligned16(x) || (x_pixel_stride & 3)) return BTS_EALIGN;
+    PwfParams p;
+    p.x = x; p.xs = x_pixel_stride; p.M = M; p.w = w; p.s_out = s_out; p.s_in = s_in; p.Cout = Cout; p.act = act;
+    p.out = out; p.os = out_pixel_stride;
+    p.ncog = (Cout + 3) / 4;
+    p.lg = 0;
+    while ((1 << p.lg) < p.ncog) ++p.lg;
+    const long long ppb = 256 >> p.lg;
+    long long grid = (M + ppb - 1) / ppb;
+    const long long cap = (long long)bts_num_sms() * 8;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Cin) {
+        case 8: pw_fwd_kernel<8><<<(int)grid, 256, 0, st>>>(p); break;
+        case 16: pw_fwd_kernel<16><<<(int)grid, 256, 0, st>>>(p); break;
+        case 32: pw_fwd_kernel<32><<<(int)grid, 256, 0, st>>>(p); break;
+        default: pw_fwd_kernel<64><<<(int)grid, 256, 0, st>>>(p); break;
+    }
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+

@@ -276,6 +276,12 @@ int bts_avgpool2_bwd(const float *g, long long g_pixel_stride, int B, int Hout, 
 /* ---- weight gradient of the narrow 1x1 convolutions of the reduction heads (bts.py:83-108) on CUDA cores (csrc/pointwise.cu):
  * dW[co,ci] = sum_p dY[p,co]*x[p,ci] for Cin in {8,16,32,64}, Cout <= 32 -- HBM-bound, deterministic two-pass reduction.
  * workspace: bts_conv_pw_wgrad_workspace_floats(Cin, Cout) floats; dw addressed by its (co, ci) strides in floats. */
+/* Forward / dgrad of the same narrow 1x1 layers on CUDA cores (HBM-bound): out[p, co] = act(sum_ci x[p, ci] * W[co, ci]),
+ * Cin in {8,16,32,64}, Cout <= 64; (s_out, s_in) are the element strides of W[out, in] -- for dgrad pass the conv weight's
+ * (s_ci, s_co) and dY as x.  act: 0 none, 1 ELU, 2 sigmoid.  Replaces the tensor engine for reduc1x1/2x2/4x4 (bts.py:83-108). */
+int bts_conv_pw_fwd_eligible(int Cin, int Cout);
+int bts_conv_pw_fwd(const float *x, long long x_pixel_stride, long long M, int Cin, const float *w, long long s_out,
+                    long long s_in, int Cout, int act, float *out, long long out_pixel_stride, void *stream);
 int bts_conv_pw_wgrad_eligible(int Cin, int Cout);
 long long bts_conv_pw_wgrad_workspace_floats(int Cin, int Cout);
 int bts_conv_pw_wgrad(const float *x, long long x_pixel_stride, const float *dy, long long dy_pixel_stride, long long M,

@@ -206,6 +206,39 @@ def test_wgrad_pointwise_wide_tile_on_shifted_dy_kernel(w2_mode, Cin, Cout, H, W
     assert err < 2e-5, err
 
 
+@pytest.mark.parametrize("Cin,Cout,act", [(32, 16, "elu"), (16, 8, "elu"), (8, 3, None), (64, 32, "elu"), (64, 12, None),
+                                           (8, 1, "sigmoid"), (16, 64, None), (32, 64, "elu")])
+def test_pointwise_forward_and_dgrad_cuda_core_kernel(Cin, Cout, act, monkeypatch):
+    """narrow 1x1 layers of the reduction heads: forward (+ELU / sigmoid) and dgrad on the HBM-bound CUDA-core kernel
+    (bts_conv_pw_fwd) vs fp64, NHWC tensors, channel slices of wider slabs as input and output"""
+    from bts_b200 import conv
+    monkeypatch.setattr(conv, "PW_MIN_PIXELS", 0)
+    g = torch.Generator().manual_seed(31 + Cin + Cout)
+    slab = torch.randn(3, Cin + 8, 17, 23, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    x = slab[:, 4:4 + Cin]
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).cuda()
+    before = len(conv.trace_log) if conv.TRACE else None
+    y = conv.conv2d_tc(x, w, 1, 0, 1, act=act)
+    ref = F.conv2d(x.double().cpu(), w.double().cpu())
+    if act == "elu":
+        ref = F.elu(ref)
+    elif act == "sigmoid":
+        ref = torch.sigmoid(ref)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-5
+    # into a channel slice of a wider output slab
+    oslab = torch.zeros(3, Cout + 4, 17, 23).cuda().contiguous(memory_format=torch.channels_last)
+    conv.conv2d_tc(x, w, 1, 0, 1, act=act, out=oslab[:, :Cout])
+    assert torch.equal(oslab[:, :Cout], y) and float(oslab[:, Cout:].abs().sum()) == 0.0
+    # dgrad = the transposed operator
+    gy = torch.randn(3, Cout, 17, 23, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    gx = conv.conv2d_tc(gy, w, 1, 0, 1, transpose_flip=True)
+    gref = F.conv_transpose2d(gy.double().cpu(), w.double().cpu())
+    assert gx.shape == gref.shape
+    assert (gx.cpu().double() - gref).abs().max() / gref.abs().max() < 1e-5
+    assert before is None or len(conv.trace_log) > before
+
+
 @pytest.mark.parametrize("Cin,Cout", [(32, 16), (16, 8), (8, 3), (64, 32), (64, 12), (8, 1)])
 def test_pointwise_wgrad_cuda_core_kernel(Cin, Cout, monkeypatch):
     """narrow 1x1 layers of the reduction heads: dW on the HBM-bound CUDA-core kernel (csrc/pointwise.cu) vs fp64"""
