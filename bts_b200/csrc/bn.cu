@@ -318,8 +318,12 @@ extern "C" int bts_bn_stats(const float *x, long long x_pixel_stride, long long 
     if (!x || !sum || !sumsq || M < 1 || C < 1) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(sum, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(sumsq, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    if (sumsq == sum + C) {
+        if ((e = cudaMemsetAsync(sum, 0, sizeof(double) * 2 * C, st)) != cudaSuccess) return (int)e;
+    } else {
+        if ((e = cudaMemsetAsync(sum, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(sumsq, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    }
     const int cg = (C + 255) / 256;
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
@@ -354,8 +358,12 @@ extern "C" int bts_bn_bwd_reduce(const float *x, long long x_pixel_stride, const
     if (!x || !g || !scale || !shift || !mean || !invstd || !S1 || !S2 || !coef || M < 1 || C < 1) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(S2, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    if (S2 == S1 + C) {                         // the usual [2, C] tensor: one memset
+        if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * 2 * C, st)) != cudaSuccess) return (int)e;
+    } else {
+        if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(S2, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    }
     const int cg = (C + 255) / 256;
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);
@@ -380,8 +388,12 @@ extern "C" int bts_bn_relu_bwd_fused(const float *x, long long x_pixel_stride, c
     if ((K0 == nullptr) != (K1 == nullptr)) return BTS_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemsetAsync(S2, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    if (S2 == S1 + C) {                         // the usual [2, C] tensor: one memset
+        if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * 2 * C, st)) != cudaSuccess) return (int)e;
+    } else {
+        if ((e = cudaMemsetAsync(S1, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(S2, 0, sizeof(double) * C, st)) != cudaSuccess) return (int)e;
+    }
     const int cg = (C + 255) / 256;
     const int rows = reduce_rows(M, cg);
     dim3 grid((unsigned)((M + rows - 1) / rows), (unsigned)cg);

@@ -173,15 +173,25 @@ class _DenseBlockFn(torch.autograd.Function):
             sums[:, :C0] = bn_stats(slab[:, :C0])
         saved_b, saved_st = [], []
         C = C0
+        # the zeroed [2, C] accumulators of the epilogue statistics of every layer, carved out of ONE zero fill
+        zoff = [0]
+        zbuf = torch.zeros(2 * sum(params[6 * li + 2].shape[0] + growth for li in range(len(layers))), device=x.device,
+                           dtype=torch.float64) if training else None
+
+        def zeros2(c):
+            v = zbuf[zoff[0]:zoff[0] + 2 * c].view(2, c)
+            zoff[0] += 2 * c
+            return v
+
         for li, layer in enumerate(layers):
             w1, w2 = params[6 * li + 2], params[6 * li + 5]
             st1 = bn_finalize(sums[:, :C] if training else None, n, layer.norm1, training)
             epi = training and EPI_STATS and w1.shape[0] <= 256 and growth <= 256
-            sb = torch.zeros((2, w1.shape[0]), device=x.device, dtype=torch.float64) if epi else None
+            sb = zeros2(w1.shape[0]) if epi else None
             b = conv.conv2d_tc(slab[:, :C], w1, 1, 0, 1, pre_scale=st1[0], pre_shift=st1[1], pre_relu=True, stats=sb)
             st2 = bn_finalize((sb if epi else bn_stats(b)) if training else None, n, layer.norm2, training)
             more = training and li + 1 < len(layers)
-            sn = torch.zeros((2, growth), device=x.device, dtype=torch.float64) if (epi and more) else None
+            sn = zeros2(growth) if (epi and more) else None
             conv.conv2d_tc(b, w2, 1, 1, 1, pre_scale=st2[0], pre_shift=st2[1], pre_relu=True, out=slab[:, C:C + growth],
                            stats=sn)
             if more:
