@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc 
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_LIMIT = 232448;          // 227 KB opt-in maximum per CTA
 constexpr int BAR_BYTES = 256;
-constexpr int STAT_BYTES = 2 * MAX_N * 4;   // per-CTA fp32 partial sums of the epilogue statistics
+// per-CTA partial sums of the epilogue statistics: fp64, one private set per epilogue warp ([4][2][n_tile]) -- no atomics,
+// fixed accumulation order (round 2: the fp32 shared-memory atomics made a training step irreproducible at 3e-3 of the
+// gradient, tools/determinism_probe.py)
+constexpr int STAT_SETS = 4;
 
 // PRE: 0 none, 1 ReLU, 2 affine, 3 affine + ReLU (compile-time so the per-element producer code carries no dead ops)
 // UP : nearest x2 up-sample folded into the address map;  VEC: 16-byte aligned rows (float4 loads)
@@ -256,13 +259,13 @@ __global__ void __launch_bounds__(192 + 128 * G, 1) conv_tc_kernel(const ConvPar
     auto tmem_full = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bar0 + 8u * (3 * MAX_STAGES + 2 + a); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * MAX_STAGES + 4);
-    float *s_stat = reinterpret_cast<float *>(sm + bar_off + BAR_BYTES);      // [2][MAX_N], only when p.stat_sum
+    double *s_stat = reinterpret_cast<double *>(sm + bar_off + BAR_BYTES);    // [4 warps][2][n_tile], only when p.stat_sum
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = p.n_tile;
     const int KB = p.KB;
     if (p.stat_sum)
-        for (int i = threadIdx.x; i < 2 * MAX_N; i += NUM_THREADS) s_stat[i] = 0.f;
+        for (int i = threadIdx.x; i < STAT_SETS * 2 * n_tile; i += NUM_THREADS) s_stat[i] = 0.0;
     // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...   (tile -> m_tile = tile / n_tiles, nt = tile % n_tiles)
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_kb = my_tiles * KB;          // host guarantees < 2^31
@@ -817,9 +820,10 @@ __global__ void __launch_bounds__(192 + 128 * G, 1) conv_tc_kernel(const ConvPar
                     s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
                     s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
                     const int col = cc + (lane >> 1);             // lane bits 4..1 = column within the 16-column group
-                    if ((lane & 1) == 0 && nt * n_tile + col < p.Cout) {
-                        atomicAdd(&s_stat[col], s1[0]);
-                        atomicAdd(&s_stat[MAX_N + col], s2[0]);
+                    if ((lane & 1) == 0 && nt * n_tile + col < p.Cout) {       // this (warp, lane) owns the slot: plain adds
+                        double *mine = s_stat + (size_t)q * 2 * n_tile;
+                        mine[col] += (double)s1[0];
+                        mine[n_tile + col] += (double)s2[0];
                     }
                 }
             }
@@ -829,12 +833,17 @@ __global__ void __launch_bounds__(192 + 128 * G, 1) conv_tc_kernel(const ConvPar
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int c = (int)threadIdx.x - (NUM_THREADS - EPI_THREADS); c < n_tile; c += EPI_THREADS) {
                     const int ch = nt * n_tile + c;
-                    if (ch < p.Cout) {
-                        atomicAdd(p.stat_sum + ch, (double)s_stat[c]);
-                        atomicAdd(p.stat_sumsq + ch, (double)s_stat[MAX_N + c]);
+                    double t1 = 0.0, t2 = 0.0;
+                    for (int w = 0; w < STAT_SETS; ++w) {                // fixed order over the four warps
+                        t1 += s_stat[(size_t)w * 2 * n_tile + c];
+                        t2 += s_stat[(size_t)w * 2 * n_tile + n_tile + c];
+                        s_stat[(size_t)w * 2 * n_tile + c] = 0.0;
+                        s_stat[(size_t)w * 2 * n_tile + n_tile + c] = 0.0;
                     }
-                    s_stat[c] = 0.f;
-                    s_stat[MAX_N + c] = 0.f;
+                    if (ch < p.Cout) {
+                        atomicAdd(p.stat_sum + ch, t1);
+                        atomicAdd(p.stat_sumsq + ch, t2);
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -844,8 +853,13 @@ __global__ void __launch_bounds__(192 + 128 * G, 1) conv_tc_kernel(const ConvPar
         if (p.stat_sum && p.n_tiles == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
             for (int c = (int)threadIdx.x - (NUM_THREADS - EPI_THREADS); c < p.Cout; c += EPI_THREADS) {
-                atomicAdd(p.stat_sum + c, (double)s_stat[c]);
-                atomicAdd(p.stat_sumsq + c, (double)s_stat[MAX_N + c]);
+                double t1 = 0.0, t2 = 0.0;
+                for (int w = 0; w < STAT_SETS; ++w) {                    // fixed order over the four warps
+                    t1 += s_stat[(size_t)w * 2 * n_tile + c];
+                    t2 += s_stat[(size_t)w * 2 * n_tile + n_tile + c];
+                }
+                atomicAdd(p.stat_sum + c, t1);
+                atomicAdd(p.stat_sumsq + c, t2);
             }
         }
     }
@@ -1059,7 +1073,7 @@ static int conv_fwd_impl(const float *x, long long x_pixel_stride, int B, int Hs
     // shared-memory plan: stage = A hi/lo (2 x 16 KB) + B hi/lo (2 x n_tile x 128 B); as many stages as fit
     p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.n_tile * 128;
     const int pre_bytes = pre >= 2 ? p.KC * 32 * 8 : 0;
-    const int stat_bytes = stat_sum ? STAT_BYTES : 0;
+    const int stat_bytes = stat_sum ? STAT_SETS * 2 * p.n_tile * 8 : 0;
     p.stages = (SMEM_LIMIT - 1024 - BAR_BYTES - pre_bytes - stat_bytes) / p.stage_bytes;
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     if (p.stages < 2) return BTS_EINVAL;

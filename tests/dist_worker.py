@@ -38,13 +38,10 @@ def main():
     crit = bts.silog_loss(0.85)
     crit(solo(x, focal)[4], gt, gt > 0.1).backward()
     crit(ddp(x, focal)[4], gt, gt > 0.1).backward()
-    # `solo` and `par` run the same arithmetic on the same shard, but not bit-identically: the BatchNorm statistics are reduced
-    # with atomics (summation order varies -> last-ulp differences of a scale), and a random-init train-mode network of
-    # ~160 layers with batch 2 amplifies that by 3-4 orders of magnitude; parameters whose gradient is a small difference of
-    # large terms (BatchNorm weights deep in a block) show it most (measured on B200: 5.4e-3 on ONE norm1.weight, median
-    # < 1e-5).  A wrong collective (missing all-reduce, sum instead of mean, stale bucket) shows as an error of order
-    # 0.3-1 on EVERY parameter.  Hence: whole-gradient error < 2e-3, median per-parameter error < 1e-4, no parameter > 5e-2.
-    worst, errs, num, den = 0.0, [], 0.0, 0.0
+    # `solo` and `par` run the same arithmetic on the same shard; the engine is bit-reproducible run to run
+    # (tools/determinism_probe.py: every reduction has a fixed order or runs in fp64), so what remains between them is the
+    # all-reduce itself: NCCL's ring sum of the world's gradients in fp32 vs this test's own all_reduce + divide.
+    worst, errs = 0.0, []
     for (k, a), (_, b) in zip(solo.named_parameters(), par.named_parameters()):
         if a.grad is None:
             assert b.grad is None or float(b.grad.abs().sum()) == 0.0, k
@@ -53,13 +50,9 @@ def main():
         dist.all_reduce(mean)
         mean /= world
         err = float((b.grad - mean).norm() / mean.norm().clamp_min(1e-20))
-        num += float((b.grad - mean).double().pow(2).sum())
-        den += float(mean.double().pow(2).sum())
         worst = max(worst, err)
         errs.append(err)
-        assert err < 5e-2, "%s: DDP gradient differs from the mean of the per-shard gradients by %.3g" % (k, err)
-    assert (num / den) ** 0.5 < 2e-3, "whole-gradient DDP error %.3g" % ((num / den) ** 0.5)
-    assert sorted(errs)[len(errs) // 2] < 1e-4, "median DDP gradient error %.3g" % sorted(errs)[len(errs) // 2]
+        assert err < 1e-5, "%s: DDP gradient differs from the mean of the per-shard gradients by %.3g" % (k, err)
     # (1b) the B200-native schedule of bench.py -- bts_b200.dist.FlatGradReducer -- produces the same averaged gradients
     from bts_b200 import dist as D
     flat_m = build()
@@ -70,7 +63,7 @@ def main():
         if b.grad is None:
             continue
         err = float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-20))
-        assert err < 5e-2, "%s: flat reducer vs DDP %.3g" % (k, err)
+        assert err < 1e-5, "%s: flat reducer vs DDP %.3g" % (k, err)
     bb = D.FlatBufferBroadcaster(flat_m)
     bb.broadcast(0)
     fb = (flat_m.encoder.base_model.norm0 if hasattr(flat_m.encoder.base_model, "norm0") else flat_m.encoder.base_model.bn1)
