@@ -101,6 +101,7 @@ SIGNATURES = {
     "bts_conv_c1_wgrad": [_p, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _p, _ll, _ll, _ll, _p],
     "bts_bn_stats": [_p, _ll, _ll, _i, _p, _p, _p],
     "bts_bn_finalize": [_p, _p, _ll, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "bts_bn_finalize_track": [_p, _p, _ll, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_fold": [_i, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_reduce": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "bts_bn_relu_bwd_apply": [_p, _ll, _p, _ll, _ll, _i, _p, _p, _p, _p, _ll, _i, _p],

@@ -201,8 +201,9 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sum, const double 
                                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                    float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
                                    float *__restrict__ scale, float *__restrict__ shift, float *__restrict__ mean,
-                                   float *__restrict__ invstd) {
+                                   float *__restrict__ invstd, long long *__restrict__ num_batches_tracked) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;     // nn.BatchNorm2d.num_batches_tracked += 1
     if (c >= C) return;
     const double m = sum[c] / (double)N;
     double var = sumsq[c] / (double)N - m * m;     // biased, used for normalisation
@@ -338,7 +339,21 @@ extern "C" int bts_bn_finalize(const double *sum, const double *sumsq, long long
                                float *scale, float *shift, float *mean, float *invstd, void *stream) {
     if (!sum || !sumsq || !scale || !shift || !mean || !invstd || N < 1 || C < 1) return BTS_EINVAL;
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, N, C, gamma, beta, eps, momentum,
-                                                                          running_mean, running_var, scale, shift, mean, invstd);
+                                                                          running_mean, running_var, scale, shift, mean, invstd,
+                                                                          nullptr);
+    BTS_LAUNCH_CHECK();
+    return 0;
+}
+
+// the same, also incrementing the module's int64 `num_batches_tracked` buffer in the same launch
+extern "C" int bts_bn_finalize_track(const double *sum, const double *sumsq, long long N, int C, const float *gamma,
+                                     const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                                     long long *num_batches_tracked, float *scale, float *shift, float *mean, float *invstd,
+                                     void *stream) {
+    if (!sum || !sumsq || !scale || !shift || !mean || !invstd || N < 1 || C < 1) return BTS_EINVAL;
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, N, C, gamma, beta, eps, momentum,
+                                                                          running_mean, running_var, scale, shift, mean, invstd,
+                                                                          num_batches_tracked);
     BTS_LAUNCH_CHECK();
     return 0;
 }

@@ -219,6 +219,9 @@ int bts_bn_stats(const float *x, long long x_pixel_stride, long long M, int C, d
 int bts_bn_finalize(const double *sum, const double *sumsq, long long N, int C, const float *gamma, const float *beta,
                     float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                     float *mean, float *invstd, void *stream);
+int bts_bn_finalize_track(const double *sum, const double *sumsq, long long N, int C, const float *gamma, const float *beta,
+                          float eps, float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
+                          float *scale, float *shift, float *mean, float *invstd, void *stream);   /* + num_batches_tracked += 1 */
 int bts_bn_fold(int C, const float *gamma, const float *beta, float eps, const float *running_mean,
                 const float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream);
 int bts_bn_relu_bwd_reduce(const float *x, long long x_pixel_stride, const float *g, long long g_pixel_stride,
