@@ -118,7 +118,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.p = [], None
+        self.rows, self.p, self.start = [], None, 0
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
@@ -132,6 +132,10 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """the timed region starts now: earlier samples are dropped"""
+        self.start = len(self.rows)
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -143,7 +147,7 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.start:]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -755,13 +759,25 @@ def _run_ours(args):
         return loss
 
     def timed(fn, K, Wm):
+        if world > 1:
+            # exercise the collectives of the bracket (barrier, MAX all-reduce) once BEFORE the warm-up steps: their first use
+            # sets up NCCL state lazily, and at 8 GPUs the aftermath landed in the first timed step of one rank (+90-120 ms on
+            # the max-over-ranks span, absent from rank 0's per-step events and from the second timed() call)
+            dist.barrier()
+            dist.all_reduce(torch.zeros(1, device=dev), op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
         for i in range(Wm):
             fn(i)
+        # rank 0 forks nvidia-smi BEFORE the barrier: the fork of a process with a CUDA context costs tens of ms, and with
+        # N > 1 every other rank would wait for rank 0 in the first all-reduce -- inside ITS timed span (measured: +86 ms on
+        # the max-over-ranks span of a 10-step run at 8 GPUs)
+        sampler = ClockSampler(local) if rank == 0 else None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.mark()
         l0 = _lib.launches
         st = torch.cuda.current_stream()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
@@ -775,6 +791,9 @@ def _run_ours(args):
         torch.cuda.synchronize()
         ms = torch.tensor([marks[0].elapsed_time(marks[K])], device=dev)
         if world > 1:
+            spans = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(spans, ms)
+            timed.rank_spans_ms = [round(float(t), 2) for t in spans]      # reported: shows rank skew / one-off stalls
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
         clocks = sampler.stop() if sampler else None
@@ -782,6 +801,7 @@ def _run_ours(args):
 
     K, Wm = args.steps, max(args.warmup, 3)
     ms, launches, clocks, per = timed(lambda i: step(i, img, focal, gt), K, Wm)
+    rank_spans = getattr(timed, "rank_spans_ms", None)
 
     def e2e_step(i):
         if graphed is not None:                  # H2D straight into the graph's static input buffers
@@ -811,7 +831,8 @@ def _run_ours(args):
         "e2e": {"value": world * B * K / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e / K, "ms_per_step_median": statistics.median(per_e)},
         "repeats": {"ms_per_step_median": statistics.median(per), "ms_per_step_min": per[0], "ms_per_step_max": per[-1],
-                    "n": K, "note": "rank-0 per-step CUDA-event durations inside the timed region"},
+                    "n": K, "note": "rank-0 per-step CUDA-event durations inside the timed region",
+                    "rank_spans_ms": rank_spans},
         "gpu_launches": launches, "clocks": clocks,
     }
     if selfcheck is not None:
